@@ -1,0 +1,182 @@
+/* qmps_b200 -- C ABI of the B200-native classical inner loop of qmps.
+ *
+ * The reference (fergusfinn/qmps) is pure Python and has no FFI; its boundary for
+ * this path is the set of Python callables of SURVEY.md section 8(b).  Every entry
+ * point below names the reference callable (file:line under the reference root) it
+ * replaces.  INTEGRATION.md shows the ctypes stubs a maintainer adds to qmps/tools.py
+ * etc. to route those callables here.
+ *
+ * Conventions
+ *   - complex numbers are interleaved (re, im) pairs: complex128 = 2 x double
+ *     (numpy.complex128 / cuDoubleComplex layout), complex64 = 2 x float.
+ *   - `dtype`: QMPS_C128 or QMPS_C64 selects the arithmetic AND the element type of
+ *     every complex/real array argument (theta and shift arrays are always double).
+ *   - all arrays are contiguous, batch-major, row-major; tensors A are [d][D][D]
+ *     with A[s][i][j] as in unitary_to_tensor (qmps/tools.py:151-154).
+ *   - functions without the _host suffix take DEVICE pointers and enqueue work on
+ *     `stream` (a cudaStream_t passed as void*; NULL = default stream) without
+ *     synchronising.  *_host functions take HOST pointers, do the copies themselves
+ *     and return after the results are in the caller's buffers.
+ *   - return value: 0 on success, a negative QMPS_ERR_* code otherwise
+ *     (qmps_last_error() gives the message).  Per-problem numerical conditions are
+ *     reported in the optional int32 `status` array, never by failing the call:
+ *       QMPS_ST_OK          0
+ *       QMPS_ST_NOT_PD      1  cholesky(r) failed: the reference raises
+ *                              numpy.linalg.LinAlgError here (qmps/tools.py:182)
+ *       QMPS_ST_NO_CONVERGE 2  QR iteration hit its sweep limit
+ *       QMPS_ST_SINGULAR    3  degenerate leading eigenvalue (fixed point not unique)
+ *   - output pointers documented as "optional" may be NULL.
+ */
+#ifndef QMPS_B200_H
+#define QMPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMPS_C128 0
+#define QMPS_C64 1
+
+#define QMPS_ST_OK 0
+#define QMPS_ST_NOT_PD 1
+#define QMPS_ST_NO_CONVERGE 2
+#define QMPS_ST_SINGULAR 3
+
+#define QMPS_ERR_ARG (-1)      /* invalid argument */
+#define QMPS_ERR_CUDA (-2)     /* CUDA runtime error */
+#define QMPS_ERR_UNSUPPORTED (-3)
+
+/* gate codes of an ansatz program (qmps/represent.py:268-423 gate lists as data) */
+#define QMPS_G_RZ 0
+#define QMPS_G_RX 1
+#define QMPS_G_RY 2
+#define QMPS_G_H 3
+#define QMPS_G_CNOT 4
+#define QMPS_G_SWAP 5
+#define QMPS_G_CZ 6
+#define QMPS_G_XPOW 7
+#define QMPS_G_ZZPOW 8
+#define QMPS_G_XXPOW 9
+#define QMPS_G_YYPOW 10
+#define QMPS_G_X 11
+#define QMPS_G_Z 12
+
+/* one gate: angle (or exponent) = scale * theta[param] + offset; param < 0: constant */
+typedef struct qmps_gate_op {
+  int32_t code;
+  int32_t q0;     /* target / control / first qubit (qubit 0 = most significant) */
+  int32_t q1;     /* CNOT target / second qubit */
+  int32_t param;
+  double scale;
+  double offset;
+} qmps_gate_op;
+
+const char* qmps_version(void);
+const char* qmps_last_error(void);
+/* number of visible CUDA devices (0 if none); never fails */
+int qmps_device_count(void);
+
+/* a1  unitary_to_tensor (qmps/tools.py:151-154): U [N][2D][2D] -> A [N][2][D][D] */
+int qmps_unitary_to_tensor(int D, int64_t N, const void* U, void* A, int dtype, void* stream);
+
+/* a2  tensor_to_unitary + unitary_extension (qmps/tools.py:123-148, 76-94):
+ *     A [N][d][D][D] (left-canonical) -> U [N][dD][dD], U[:, :D] = iso exactly; the
+ *     remaining columns are a Householder completion (any orthonormal completion is
+ *     valid: the reference's own null_space columns are not unique either). */
+int qmps_tensor_to_unitary(int d, int D, int64_t N, const void* A, void* U, int dtype, void* stream);
+
+/* a3  environment_to_unitary (qmps/tools.py:97-108): v [N][n] -> V [N][n][n] with
+ *     V[:,0] = v/|v| exactly, Householder completion. */
+int qmps_environment_to_unitary(int n, int64_t N, const void* v, void* V, int dtype, void* stream);
+
+/* a4/a5  TransferMatrix(A).eigs() + cholesky (qmps/tools.py:176-182):
+ *     in: A [N][d][D][D] (in_is_full_U = 0) or U [N][2D][2D] (in_is_full_U = 1, d = 2).
+ *     assume_left_canonical = 1: eta = 1 is known, direct fixed-point solve.
+ *     assume_left_canonical = 0: full eigen-solve (any A), r rotated to Hermitian.
+ *     out (all optional): eta [N] complex, r [N][D][D] Hermitian trace 1,
+ *     C [N][D][D] lower Cholesky factor (r = C C^dagger), status [N]. */
+int qmps_env_exact(int d, int D, int64_t N, const void* in, int in_is_full_U,
+                   int assume_left_canonical, void* eta, void* r, void* C, int32_t* status,
+                   int dtype, void* stream);
+/* same with HOST buffers; chunked, copies overlapped with compute */
+int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_U,
+                        int assume_left_canonical, void* eta, void* r, void* C, int32_t* status,
+                        int dtype, int device);
+
+/* a6  Map(A,B).right_fixed_point() / .left_fixed_point() (xmps; call sites
+ *     qmps/time_evolve_tools.py:87, qmps/loschmidts/time_evo.py:79-82):
+ *     A [NA][d][D][D], B [NB][d][D][D].
+ *     pair_mode 0: problem i uses A[min(i,NA-1)] , B[min(i,NB-1)], N = max(NA,NB)
+ *     pair_mode 1: outer product, problem (ia, ib) -> index ia*NB + ib
+ *     left = 0: right fixed point (x, r); left = 1: left fixed point (x, l).
+ *     out (optional): eta [N] complex, vec [N][D][D] unit Frobenius norm with tr >= 0,
+ *     cost [N] = -sqrt|eta| (a11, qmps/loschmidts/time_evo.py:75-116),
+ *     echo [N] = -log|eta|^2, fid [N] = |eta|^2 (a8, qmps/time_evolve_tools.py:84-91),
+ *     status [N]. */
+int qmps_fixed_point(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B,
+                     int pair_mode, int left, void* eta, void* vec, void* cost, void* echo,
+                     void* fid, int32_t* status, int dtype, void* stream);
+
+/* a7  merge (qmps/time_evolve_tools.py:20-23): A [NA][d1][D][D], B [NB][d2][D][D] ->
+ *     M [N][d1*d2][D][D], N = max(NA,NB) (a batch of 1 broadcasts).
+ *     W (optional) [NW][d1*d2][d1*d2]: M <- tensordot(W, M, [1,0])
+ *     (qmps/loschmidts/time_evo.py:79); with NW > 1 and NA = NB = 1 the output is
+ *     one block per gate. */
+int qmps_merge(int d1, int d2, int D, int64_t NA, const void* A, int64_t NB, const void* B,
+               int64_t NW, const void* W, void* M, int dtype, void* stream);
+
+/* a14 ansatz gate lists (qmps/represent.py:268-423): theta [N][P] (double) -> A
+ *     [N][2][D][D] (full_unitary = 0) or U [N][2D][2D] (full_unitary = 1);
+ *     nq = log2(D)+1 qubits.  `ops` is a HOST array. */
+int qmps_ansatz(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, const double* theta,
+                int full_unitary, void* out, int dtype, void* stream);
+
+/* a9 + a12  energy cost (qmps/ground_state.py:150-168, 251-266) with the rotosolve
+ *     shift fan-out (qmps/rotosolve.py:175, qmps/tools.py:432-438) fused in:
+ *     problem (n, s) evaluates theta[n] + shifts[s] * e_coord.
+ *     ops/nops/nq as qmps_ansatz; hmat: DEVICE [4][4] complex; shifts: HOST
+ *     [nshift] (NULL / nshift = 0: one unshifted evaluation, coord ignored).
+ *     out: energy [N][max(nshift,1)] real, status optional same shape. */
+int qmps_energy_theta(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P,
+                      const double* theta, const void* hmat, int coord, const double* shifts,
+                      int nshift, void* energy, int32_t* status, int dtype, void* stream);
+/* energy from tensors: two_site = 0: in = A [N][2][D][D], M = merge(A,A), env of E_AA;
+ *     two_site = 1: in = M [N][4][D][D] (merge(A1,A2)), env of E_MM
+ *     (qmps/ground_state.py:291-331). */
+int qmps_energy_tensor(int D, int64_t N, const void* in, int two_site, const void* hmat,
+                       void* energy, int32_t* status, int dtype, void* stream);
+
+/* a12  rotosolve closed forms on DEVICE arrays of costs:
+ *     nshift = 3: cost [N][3] at shifts (0, +pi/2, -pi/2) -> theta_star [N]
+ *       = -pi/2 - atan2(2 e0 - e+ - e-, e+ - e-) (qmps/rotosolve.py:175) and, if
+ *       theta_io is given ([N][P], coordinate `coord`), the wrapped in-place update
+ *       of qmps/rotosolve.py:176-177.
+ *     nshift = 6: cost [N][6] at shifts (0, pi, pi/2, -pi/2, pi/4, -pi/4) -> fit [N][8]
+ *       = (a, b, c, d, P, u, Q, v) of qmps/tools.py:434-447 and theta_star = global
+ *       minimiser of P sin(2x+u) + Q sin(x+v) on [-pi, pi].
+ *     All arrays double. */
+int qmps_rotosolve_fit(int64_t N, int nshift, const double* cost, double* theta_star,
+                       double* fit, double* theta_io, int P, int coord, void* stream);
+
+/* a13 exact TFIM Loschmidt rate function loschmidt(t, g0, g1)
+ *     (qmps/loschmidts/exact_loschmidt.py:6-20): t [NT] -> out [NT], DEVICE doubles. */
+int qmps_loschmidt_rate(int64_t NT, const double* t, double g0, double g1, double* out, void* stream);
+
+/* cfg 5  classical power method (qmps.ipynb cells 29-32): K normalised applications
+ *     r <- sum_s A_s r B_s^dagger / |.|_F.  A, B [N][d][D][D]; r_io [N][D][D] (start
+ *     vector in, r_K out); rayleigh [N] complex = <r_K, E r_K> (optional). */
+int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K,
+                  void* rayleigh, int dtype, void* stream);
+
+/* (e)  local part of the final cost reduction: (min cost, argmin + index_offset) of a
+ *     DEVICE array, written to DEVICE best_cost[1] / best_index[1]; the cross-rank
+ *     step is one NCCL all-gather of 16 bytes per rank (qmps_b200/dist.py). */
+int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* best_cost,
+                int64_t* best_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMPS_B200_H */

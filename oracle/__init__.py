@@ -1,0 +1,40 @@
+"""CPU oracle for the qmps classical hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the shipped
+product: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it, and there only as
+the checker or as the timed CPU baseline.  The product (``qmps_b200``) never
+imports this package and fails loudly when its CUDA library is missing.
+
+The oracle is a numpy/scipy restatement (complex128) of the reference's
+algorithm for the path SURVEY.md section 8 names, each function citing the
+reference ``file:line`` it follows.
+
+Parity pinning status (see DESIGN.md section "Oracle"):
+
+* PINNED against the reference's own code run in the build container
+  (``oracle/make_golden.py`` imports ``/root/reference/qmps/tools.py`` and
+  ``qmps/loschmidts/exact_loschmidt.py`` under stub modules and records their
+  outputs in ``tests/golden/``): ``unitary_to_tensor``, ``tensor_to_unitary``,
+  ``unitary_extension``, ``environment_to_unitary``,
+  ``environment_from_unitary``, ``from_real_vector``/``to_real_vector``,
+  ``direct_sum``, ``cT``, ``double_rotosolve``, ``get_env_exact`` (with the
+  un-vendored ``TransferMatrix`` supplied by this oracle), the exact TFIM
+  Loschmidt rate function.
+* PINNED against literals the reference's tests hold: the TFIM matrix of
+  ``tests/test_ground_state.py:29-38``, the exact ``E0(g)`` integral
+  ``tests/test_ground_state.py:101-102``, ``D2_gse`` of
+  ``scripts/noisy_optimization.py:93``, the known-answer environment of
+  ``new_tdvp/testTDVPStripped.py:156-170``.
+* PARITY UNPINNED: everything whose arithmetic lives in the un-vendored,
+  un-pinned third-party packages ``xmps`` (``TransferMatrix.eigs``,
+  ``Map.right_fixed_point``/``left_fixed_point``, ``iMPS.left_canonicalise``,
+  ``iMPS.overlap``) and ``cirq`` (gate matrices, circuit simulation).  Those
+  are restated from their published definitions and anchored on the
+  reference's call sites (eigen-equation, Hermitian PD ``r``, unit-Frobenius
+  fixed points, big-endian qubit order) -- see SURVEY.md A.2 / A.5.
+"""
+
+from .tensors import *      # noqa: F401,F403
+from .gates import *        # noqa: F401,F403
+from .costs import *        # noqa: F401,F403

@@ -1,0 +1,334 @@
+"""Batched device API: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is plumbing here (device memory, streams); every computation goes through the
+C ABI of ``include/qmps_b200.h`` into the hand-written sm_100a kernels.  All calls
+are stream-ordered on ``torch.cuda.current_stream()`` and do not synchronise.
+
+Shapes: tensors ``A[..., d, D, D]`` with ``A[s, i, j]`` as produced by
+``unitary_to_tensor`` (qmps/tools.py:151-154); parameter vectors ``theta[N, P]``
+(float64).
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+EnvResult = namedtuple("EnvResult", "eta r C status")
+FixedPoint = namedtuple("FixedPoint", "eta vec cost echo fid status")
+RotoFit = namedtuple("RotoFit", "theta_star fit")
+
+_CDT = {torch.complex128: L.C128, torch.complex64: L.C64}
+_RDT = {torch.complex128: torch.float64, torch.complex64: torch.float32}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _cdev(x, dtype=torch.complex128, device=None):
+    """numpy / torch -> contiguous complex CUDA tensor."""
+    L.require_device()
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return x.to(device=device, dtype=dtype).contiguous()
+
+
+def _rdev(x, device=None):
+    L.require_device()
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64)))
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return x.to(device=device, dtype=torch.float64).contiguous()
+
+
+def _dt(t):
+    if t.dtype not in _CDT:
+        raise TypeError(f"complex128 or complex64 expected, got {t.dtype}")
+    return _CDT[t.dtype]
+
+
+# ---- a1 / a2 / a3 -------------------------------------------------------------------
+def unitary_to_tensor(U):
+    """U[N, 2D, 2D] -> A[N, 2, D, D]  (qmps/tools.py:151-154)."""
+    U = _cdev(U, U.dtype if isinstance(U, torch.Tensor) and U.dtype in _CDT else torch.complex128)
+    N, m, _ = U.shape
+    D = m // 2
+    A = torch.empty((N, 2, D, D), dtype=U.dtype, device=U.device)
+    with torch.cuda.device(U.device):
+        L.check(L.load().qmps_unitary_to_tensor(D, N, _p(U), _p(A), _dt(U), _stream()), "unitary_to_tensor")
+    return A
+
+
+def tensor_to_unitary(A):
+    """A[N, d, D, D] (left-canonical) -> U[N, dD, dD], U[:, :, :D] = iso  (qmps/tools.py:123-148)."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    N, d, D, _ = A.shape
+    U = torch.empty((N, d * D, d * D), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_tensor_to_unitary(d, D, N, _p(A), _p(U), _dt(A), _stream()), "tensor_to_unitary")
+    return U
+
+
+def environment_to_unitary(v):
+    """v[N, n] -> V[N, n, n] unitary with V[:, :, 0] = v/|v|  (qmps/tools.py:97-108)."""
+    v = _cdev(v, v.dtype if isinstance(v, torch.Tensor) and v.dtype in _CDT else torch.complex128)
+    N, n = v.shape
+    V = torch.empty((N, n, n), dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        L.check(L.load().qmps_environment_to_unitary(n, N, _p(v), _p(V), _dt(v), _stream()), "environment_to_unitary")
+    return V
+
+
+# ---- a4 / a5 -------------------------------------------------------------------------
+def env_exact(A=None, U=None, assume_left_canonical=True, want_eta=True, want_r=True, want_C=True,
+              want_status=True):
+    """Exact right environment of E_AA for a batch (qmps/tools.py:176-182).
+
+    Pass either tensors ``A[N, d, D, D]`` or unitaries ``U[N, 2D, 2D]``.  Returns
+    ``EnvResult(eta[N], r[N,D,D], C[N,D,D], status[N])`` (None for outputs not asked for).
+    """
+    if (A is None) == (U is None):
+        raise ValueError("pass exactly one of A, U")
+    x = A if A is not None else U
+    x = _cdev(x, x.dtype if isinstance(x, torch.Tensor) and x.dtype in _CDT else torch.complex128)
+    N = x.shape[0]
+    if A is not None:
+        d, D = x.shape[1], x.shape[2]
+    else:
+        d, D = 2, x.shape[1] // 2
+    dev, cd = x.device, x.dtype
+    eta = torch.empty((N,), dtype=cd, device=dev) if want_eta else None
+    r = torch.empty((N, D, D), dtype=cd, device=dev) if want_r else None
+    C = torch.empty((N, D, D), dtype=cd, device=dev) if want_C else None
+    st = torch.empty((N,), dtype=torch.int32, device=dev) if want_status else None
+    with torch.cuda.device(dev):
+        L.check(L.load().qmps_env_exact(d, D, N, _p(x), int(U is not None), int(bool(assume_left_canonical)),
+                                        _p(eta), _p(r), _p(C), _p(st), _dt(x), _stream()), "env_exact")
+    return EnvResult(eta, r, C, st)
+
+
+# ---- a6 / a8 / a11 ---------------------------------------------------------------------
+def fixed_point(A, B, pair="elementwise", left=False, want_vec=True, want_costs=True, want_status=True):
+    """Leading eigenpair of the mixed transfer matrix E_AB (``Map(A,B).right_fixed_point()``).
+
+    ``pair='elementwise'``: A[NA], B[NB] broadcast (NA == NB or one of them 1).
+    ``pair='outer'``: every (A[ia], B[ib]); outputs are shaped [NA, NB, ...].
+    """
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    B = _cdev(B, A.dtype, A.device)
+    NA, d, D, _ = A.shape
+    NB = B.shape[0]
+    if B.shape[1:] != A.shape[1:]:
+        raise ValueError("A and B must share (d, D, D)")
+    outer = pair == "outer"
+    shape = (NA, NB) if outer else (max(NA, NB),)
+    dev, cd, rd = A.device, A.dtype, _RDT[A.dtype]
+    eta = torch.empty(shape, dtype=cd, device=dev)
+    vec = torch.empty(shape + (D, D), dtype=cd, device=dev) if want_vec else None
+    cost = torch.empty(shape, dtype=rd, device=dev) if want_costs else None
+    echo = torch.empty(shape, dtype=rd, device=dev) if want_costs else None
+    fid = torch.empty(shape, dtype=rd, device=dev) if want_costs else None
+    st = torch.empty(shape, dtype=torch.int32, device=dev) if want_status else None
+    with torch.cuda.device(dev):
+        L.check(L.load().qmps_fixed_point(d, D, NA, _p(A), NB, _p(B), int(outer), int(bool(left)), _p(eta), _p(vec),
+                                          _p(cost), _p(echo), _p(fid), _p(st), _dt(A), _stream()), "fixed_point")
+    return FixedPoint(eta, vec, cost, echo, fid, st)
+
+
+# ---- a7 ------------------------------------------------------------------------------
+def merge(A, B, W=None):
+    """M[(s1,s2), i, j] = (A^s1 B^s2)[i, j], optionally followed by a two-site gate
+    ``tensordot(W, M, [1, 0])`` (qmps/time_evolve_tools.py:20-23, loschmidts/time_evo.py:79)."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    B = _cdev(B, A.dtype, A.device)
+    NA, d1, D, _ = A.shape
+    NB, d2 = B.shape[0], B.shape[1]
+    NW = 0
+    if W is not None:
+        W = _cdev(W, A.dtype, A.device)
+        NW = W.shape[0]
+    N = max(NA, NB, NW)
+    M = torch.empty((N, d1 * d2, D, D), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_merge(d1, d2, D, NA, _p(A), NB, _p(B), NW, _p(W), _p(M), _dt(A), _stream()), "merge")
+    return M
+
+
+# ---- a14 -----------------------------------------------------------------------------
+def ansatz_tensors(program, theta, full_unitary=False, dtype=torch.complex128):
+    """theta[N, P] -> A[N, 2, D, D] (or U[N, 2D, 2D]) for a gate program (qmps/represent.py:268-423)."""
+    theta = _rdev(theta)
+    N, P = theta.shape
+    R = 2 ** program.nq
+    shape = (N, R, R) if full_unitary else (N, 2, R // 2, R // 2)
+    out = torch.empty(shape, dtype=dtype, device=theta.device)
+    ops = program.c_ops()
+    with torch.cuda.device(theta.device):
+        L.check(L.load().qmps_ansatz(ops, len(program), program.nq, N, P, _p(theta), int(full_unitary), _p(out),
+                                     _CDT[dtype], _stream()), "ansatz")
+    return out
+
+
+def ansatz_unitaries_host(program, theta_np):
+    """numpy theta[N, P] -> numpy U[N, 2D, 2D] (one H2D, one launch, one D2H)."""
+    U = ansatz_tensors(program, np.asarray(theta_np, dtype=np.float64), full_unitary=True)
+    return U.cpu().numpy()
+
+
+# ---- a9 / a12 --------------------------------------------------------------------------
+def _hdev(H, dtype, device):
+    H = _cdev(H, dtype, device)
+    if H.shape != (4, 4):
+        raise ValueError("H must be a 4x4 two-site Hamiltonian")
+    return H
+
+
+def energy_theta(program, theta, H, coord=None, shifts=None, want_status=False, dtype=torch.complex128):
+    """Energy cost for a batch of parameter vectors (qmps/ground_state.py:150-168, 251-266).
+
+    With ``coord``/``shifts`` the rotosolve fan-out is fused into the launch:
+    ``energy[n, s] = e(theta[n] + shifts[s] * e_coord)`` (qmps/rotosolve.py:175).
+    """
+    theta = _rdev(theta)
+    N, P = theta.shape
+    Hd = _hdev(H, dtype, theta.device)
+    sh = None
+    ns = 0
+    if shifts is not None:
+        shifts = np.ascontiguousarray(np.asarray(shifts, dtype=np.float64))
+        ns = len(shifts)
+        sh = shifts.ctypes.data
+    shape = (N, ns) if ns else (N,)
+    e = torch.empty(shape, dtype=_RDT[dtype], device=theta.device)
+    st = torch.empty(shape, dtype=torch.int32, device=theta.device) if want_status else None
+    ops = program.c_ops()
+    with torch.cuda.device(theta.device):
+        L.check(L.load().qmps_energy_theta(ops, len(program), program.nq, N, P, _p(theta), _p(Hd),
+                                           -1 if coord is None else int(coord), sh, ns, _p(e), _p(st),
+                                           _CDT[dtype], _stream()), "energy_theta")
+    return (e, st) if want_status else e
+
+
+def energy_tensor(A, H, two_site=False, want_status=False):
+    """Energy from tensors: ``A[N, 2, D, D]`` (single-site unit cell) or the two-site block
+    ``M[N, 4, D, D] = merge(A1, A2)`` (qmps/ground_state.py:291-331)."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    N, D = A.shape[0], A.shape[2]
+    Hd = _hdev(H, A.dtype, A.device)
+    e = torch.empty((N,), dtype=_RDT[A.dtype], device=A.device)
+    st = torch.empty((N,), dtype=torch.int32, device=A.device) if want_status else None
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_energy_tensor(D, N, _p(A), int(bool(two_site)), _p(Hd), _p(e), _p(st), _dt(A),
+                                            _stream()), "energy_tensor")
+    return (e, st) if want_status else e
+
+
+ROTO3_SHIFTS = (0.0, np.pi / 2, -np.pi / 2)                                   # qmps/rotosolve.py:175
+ROTO6_SHIFTS = (0.0, np.pi, np.pi / 2, -np.pi / 2, np.pi / 4, -np.pi / 4)     # qmps/tools.py:434-438
+
+
+def rotosolve_fit(costs, theta=None, coord=None):
+    """costs[N, 3|6] -> RotoFit(theta_star[N], fit[N, 8] or None).  With ``theta``/``coord``
+    the coordinate is updated in place on the device (qmps/rotosolve.py:176-177, tools.py:452)."""
+    costs = _rdev(costs)
+    N, ns = costs.shape
+    ts = torch.empty((N,), dtype=torch.float64, device=costs.device)
+    fit = torch.empty((N, 8), dtype=torch.float64, device=costs.device) if ns == 6 else None
+    P = 0
+    if theta is not None:
+        if not (theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
+            raise ValueError("theta must be a contiguous float64 CUDA tensor (updated in place)")
+        P = theta.shape[1]
+    with torch.cuda.device(costs.device):
+        L.check(L.load().qmps_rotosolve_fit(N, ns, _p(costs), _p(ts), _p(fit), _p(theta), P,
+                                            0 if coord is None else int(coord), _stream()), "rotosolve_fit")
+    return RotoFit(ts, fit)
+
+
+def rotosolve_sweeps(program, theta, H, n_sweeps=1, double=False, dtype=torch.complex128):
+    """Whole coordinate sweeps on the device for a batch of parameter vectors: for each
+    coordinate, one fused (shift fan-out + energy) launch and one closed-form update
+    launch -- no host round trip.  ``theta`` is updated in place.
+    Returns energy[N] after the last sweep."""
+    shifts = ROTO6_SHIFTS if double else ROTO3_SHIFTS
+    P = theta.shape[1]
+    for _ in range(n_sweeps):
+        for i in range(P):
+            costs = energy_theta(program, theta, H, coord=i, shifts=shifts, dtype=dtype)
+            rotosolve_fit(costs.to(torch.float64), theta, i)
+    return energy_theta(program, theta, H, dtype=dtype)
+
+
+# ---- a11 pipeline ------------------------------------------------------------------------
+def loschmidt_costs(program, theta, A0, W, dtype=torch.complex128):
+    """cost[p, k] = -sqrt|eta_2|, echo[p, k] = -log|eta_2|^2 with eta_2 the leading eigenvalue
+    of Map(W_k . merge(A0, A0), merge(B_p, B_p))  (qmps/loschmidts/time_evo.py:75-116).
+
+    theta[NP, P] parameter sets, A0[2, D, D] the state being evolved, W[NT, 4, 4] two-site
+    gates (one per time).  Four launches: ansatz, merge, gate-merge, fixed points."""
+    B = ansatz_tensors(program, theta, dtype=dtype)
+    MB = merge(B, B)
+    A0 = _cdev(A0, dtype, B.device).reshape(1, *A0.shape[-3:])
+    W = _cdev(W, dtype, B.device)
+    if W.dim() == 2:
+        W = W[None]
+    WMA = merge(A0, A0, W)
+    fp = fixed_point(WMA, MB, pair="outer", want_vec=False)
+    # outputs are [NT, NP]; the reference indexes parameter sets first
+    return fp.cost.transpose(0, 1), fp.echo.transpose(0, 1), fp.eta.transpose(0, 1)
+
+
+def overlap_theta(program, theta1, theta2, dtype=torch.complex128):
+    """Per-site fidelity |eta(E_AB)|^2 for pairs of parameter vectors
+    (``get_overlap_exact``, qmps/time_evolve_tools.py:84-91)."""
+    A = ansatz_tensors(program, theta1, dtype=dtype)
+    B = ansatz_tensors(program, theta2, dtype=dtype)
+    return fixed_point(A, B, want_vec=True)
+
+
+# ---- a13 -----------------------------------------------------------------------------
+def loschmidt_rate(t, g0, g1):
+    """Exact TFIM Loschmidt rate function for a batch of times (qmps/loschmidts/exact_loschmidt.py)."""
+    t = _rdev(t).reshape(-1)
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        L.check(L.load().qmps_loschmidt_rate(t.numel(), _p(t), float(g0), float(g1), _p(out), _stream()),
+                "loschmidt_rate")
+    return out
+
+
+# ---- cfg 5 -------------------------------------------------------------------------------
+def tm_power(A, B, K, r0=None):
+    """K normalised applications r <- sum_s A_s r B_s^dagger / |.|_F from r0 (default
+    1/sqrt(D)).  A, B [N, d, D, D].  Returns (r_K [N, D, D], rayleigh [N])."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    B = _cdev(B, A.dtype, A.device)
+    N, d, D, _ = A.shape
+    if r0 is None:
+        r = (torch.eye(D, dtype=A.dtype, device=A.device) / np.sqrt(D)).repeat(N, 1, 1).contiguous()
+    else:
+        r = _cdev(r0, A.dtype, A.device).clone()
+    ray = torch.empty((N,), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_tm_power(d, D, N, _p(A), _p(B), _p(r), int(K), _p(ray), _dt(A), _stream()), "tm_power")
+    return r, ray
+
+
+# ---- (e) -----------------------------------------------------------------------------
+def argmin(cost, index_offset=0):
+    """(min, argmin + index_offset) of a float64 CUDA vector, as 1-element CUDA tensors."""
+    cost = _rdev(cost).reshape(-1)
+    bc = torch.empty((1,), dtype=torch.float64, device=cost.device)
+    bi = torch.empty((1,), dtype=torch.int64, device=cost.device)
+    with torch.cuda.device(cost.device):
+        L.check(L.load().qmps_argmin(cost.numel(), _p(cost), int(index_offset), _p(bc), _p(bi), _stream()), "argmin")
+    return bc, bi

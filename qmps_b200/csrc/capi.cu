@@ -1,0 +1,351 @@
+// qmps_b200 C ABI (include/qmps_b200.h): argument checks, dispatch, host-buffer
+// pipelines.  No torch types here; Python reaches this through ctypes.
+#include <math.h>
+#include <stdio.h>
+#include <mutex>
+
+#include "api_common.cuh"
+#include "kernels_misc.cuh"
+
+using namespace qmps;
+using namespace qmps_host;
+
+static_assert(sizeof(qmps_gate_op) == sizeof(GateOp), "gate op layout");
+static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
+
+namespace qmps_host {
+std::string& last_error() { thread_local std::string e; return e; }
+}
+
+namespace {
+
+int env_exact_any(int d, int D, int64_t N, const void* in, int in_is_U, int assume_lc, void* eta, void* r,
+                  void* C, int32_t* status, int dtype, cudaStream_t st) {
+  if (N == 0) return 0;
+  if (D == 2 && d == 2 && assume_lc) return env_d2(N, in, in_is_U, eta, r, C, status, dtype, st);
+  EnvParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.D = D; p.N = N; p.in = in; p.in_is_U = in_is_U; p.assume_lc = assume_lc;
+  p.eta = eta; p.r = r; p.C = C; p.status = status; p.coord = -1;
+  return dtype == QMPS_C128 ? env_generic_f64(p, 0, st) : env_generic_f32(p, 0, st);
+}
+
+template <typename T>
+int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh,
+                  cudaStream_t st) {
+  if (N == 0) return 0;
+  const size_t DD = (size_t)D * D;
+  cx<T>* Tb = nullptr; cx<T>* Er = nullptr; T* invn = nullptr;
+  CK(cudaMallocAsync((void**)&Tb, sizeof(cx<T>) * N * d * DD, st));
+  CK(cudaMallocAsync((void**)&invn, sizeof(T) * N, st));
+  cx<T>* r = (cx<T>*)r_io;
+  const dim3 grid1((D + 31) / 32, (D + 31) / 32, (unsigned)(N * d)), grid2((D + 31) / 32, (D + 31) / 32, (unsigned)N);
+  auto apply = [&](cx<T>* dst) {
+    // T[b,s] = A[b,s] . r[b]   then   dst[b] = sum_s T[b,s] . B[b,s]^H
+    zgemm_tile_kernel<T><<<grid1, 256, 0, st>>>(D, D, D, 1, (const cx<T>*)A, r, 0, d, Tb, nullptr);
+    zgemm_tile_kernel<T><<<grid2, 256, 0, st>>>(D, D, D, d, Tb, (const cx<T>*)B, 1, 1, dst, nullptr);
+  };
+  for (int it = 0; it < K; ++it) {
+    apply(r);
+    inv_norm_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, invn);
+    scale_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, invn);
+  }
+  if (rayleigh) {
+    CK(cudaMallocAsync((void**)&Er, sizeof(cx<T>) * N * DD, st));
+    apply(Er);
+    vdot_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (cx<T>*)rayleigh);
+    CK(cudaFreeAsync(Er, st));
+  }
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(Tb, st));
+  CK(cudaFreeAsync(invn, st));
+  return 0;
+}
+
+}  // namespace
+
+// ================================ exported C ABI =============================================
+extern "C" {
+
+const char* qmps_version(void) { return "qmps_b200 0.1.0 (sm_100a)"; }
+const char* qmps_last_error(void) { return last_error().c_str(); }
+int qmps_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int qmps_unitary_to_tensor(int D, int64_t N, const void* U, void* A, int dtype, void* stream) {
+  if (D < 1 || N < 0 || (!U && N) || (!A && N)) return fail(QMPS_ERR_ARG, "unitary_to_tensor: bad arguments");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * 2 * D * D;
+  const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
+  if (dtype == QMPS_C128) u2t_kernel<double><<<grid, 256, 0, st>>>(D, N, (const cx<double>*)U, (cx<double>*)A);
+  else u2t_kernel<float><<<grid, 256, 0, st>>>(D, N, (const cx<float>*)U, (cx<float>*)A);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_tensor_to_unitary(int d, int D, int64_t N, const void* A, void* U, int dtype, void* stream) {
+  if (d < 1 || D < 1 || N < 0 || (!A && N) || (!U && N)) return fail(QMPS_ERR_ARG, "tensor_to_unitary: bad arguments");
+  if (d * D > 64) return fail(QMPS_ERR_UNSUPPORTED, "tensor_to_unitary: d*D > 64 not supported");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = d * D;
+  const size_t elems = (size_t)m * D * 2 + (size_t)m * m + D;
+  const int grid = (int)(N < (int64_t)sm_count() * 4 ? N : (int64_t)sm_count() * 4);
+  if (dtype == QMPS_C128) {
+    const size_t smem = elems * sizeof(cx<double>);
+    if (int rc = allow_smem(t2u_kernel<double>, smem)) return rc;
+    t2u_kernel<double><<<grid, 128, smem, st>>>(d, D, N, (const cx<double>*)A, (cx<double>*)U);
+  } else {
+    const size_t smem = elems * sizeof(cx<float>);
+    if (int rc = allow_smem(t2u_kernel<float>, smem)) return rc;
+    t2u_kernel<float><<<grid, 128, smem, st>>>(d, D, N, (const cx<float>*)A, (cx<float>*)U);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_environment_to_unitary(int n, int64_t N, const void* v, void* V, int dtype, void* stream) {
+  if (n < 1 || N < 0 || (!v && N) || (!V && N)) return fail(QMPS_ERR_ARG, "environment_to_unitary: bad arguments");
+  if (n > 4096) return fail(QMPS_ERR_UNSUPPORTED, "environment_to_unitary: n > 4096 not supported");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)(N < (int64_t)sm_count() * 4 ? N : (int64_t)sm_count() * 4);
+  if (dtype == QMPS_C128) {
+    const size_t smem = (size_t)n * sizeof(cx<double>);
+    if (int rc = allow_smem(env2u_kernel<double>, smem)) return rc;
+    env2u_kernel<double><<<grid, 256, smem, st>>>(n, N, (const cx<double>*)v, (cx<double>*)V);
+  } else {
+    const size_t smem = (size_t)n * sizeof(cx<float>);
+    if (int rc = allow_smem(env2u_kernel<float>, smem)) return rc;
+    env2u_kernel<float><<<grid, 256, smem, st>>>(n, N, (const cx<float>*)v, (cx<float>*)V);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_env_exact(int d, int D, int64_t N, const void* in, int in_is_full_U, int assume_left_canonical,
+                   void* eta, void* r, void* C, int32_t* status, int dtype, void* stream) {
+  if (N < 0 || (!in && N)) return fail(QMPS_ERR_ARG, "env_exact: bad arguments");
+  if (!is_pow2(D) || D < 1 || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "env_exact: D must be 1, 2, 4, 8 or 16");
+  if (d < 1 || d > 4) return fail(QMPS_ERR_UNSUPPORTED, "env_exact: d must be 1..4");
+  if (in_is_full_U && d != 2) return fail(QMPS_ERR_ARG, "env_exact: unitary input implies d = 2");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "env_exact: bad dtype");
+  return env_exact_any(d, D, N, in, in_is_full_U, assume_left_canonical, eta, r, C, status, dtype, (cudaStream_t)stream);
+}
+
+int qmps_fixed_point(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B, int pair_mode, int left,
+                     void* eta, void* vec, void* cost, void* echo, void* fid, int32_t* status, int dtype,
+                     void* stream) {
+  if (NA < 0 || NB < 0 || (!A && NA) || (!B && NB)) return fail(QMPS_ERR_ARG, "fixed_point: bad arguments");
+  if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: D must be 1, 2, 4, 8 or 16");
+  if (d < 1 || d > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: d must be 1..16");
+  if (pair_mode == 0 && !(NA == NB || NA == 1 || NB == 1)) return fail(QMPS_ERR_ARG, "fixed_point: batch sizes do not broadcast");
+  if (NA == 0 || NB == 0) return 0;
+  FpParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.D = D; p.NA = NA; p.NB = NB; p.A = A; p.B = B; p.pair_mode = pair_mode; p.left = left;
+  p.N = pair_mode == 1 ? NA * NB : (NA > NB ? NA : NB);
+  p.eta = eta; p.vec = vec; p.cost = cost; p.echo = echo; p.fid = fid; p.status = status;
+  if (dtype == QMPS_C128) return fixed_point_f64(p, (cudaStream_t)stream);
+  if (dtype == QMPS_C64) return fixed_point_f32(p, (cudaStream_t)stream);
+  return fail(QMPS_ERR_ARG, "fixed_point: bad dtype");
+}
+
+int qmps_merge(int d1, int d2, int D, int64_t NA, const void* A, int64_t NB, const void* B, int64_t NW,
+               const void* W, void* M, int dtype, void* stream) {
+  if (NA < 1 || NB < 1 || !A || !B || !M || (W && NW < 1)) return fail(QMPS_ERR_ARG, "merge: bad arguments");
+  if (d1 < 1 || d2 < 1 || D < 1 || d1 * d2 * D * D > 8192) return fail(QMPS_ERR_UNSUPPORTED, "merge: block too large");
+  int64_t N = NA > NB ? NA : NB;
+  if (W && NW > N) N = NW;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)(N < (int64_t)sm_count() * 8 ? N : (int64_t)sm_count() * 8);
+  if (dtype == QMPS_C128) {
+    const size_t smem = W ? sizeof(cx<double>) * d1 * d2 * D * D : 0;
+    if (int rc = allow_smem(merge_kernel<double>, smem)) return rc;
+    merge_kernel<double><<<grid, 128, smem, st>>>(d1, d2, D, NA, (const cx<double>*)A, NB, (const cx<double>*)B, NW,
+                                                  (const cx<double>*)W, N, (cx<double>*)M);
+  } else {
+    const size_t smem = W ? sizeof(cx<float>) * d1 * d2 * D * D : 0;
+    if (int rc = allow_smem(merge_kernel<float>, smem)) return rc;
+    merge_kernel<float><<<grid, 128, smem, st>>>(d1, d2, D, NA, (const cx<float>*)A, NB, (const cx<float>*)B, NW,
+                                                 (const cx<float>*)W, N, (cx<float>*)M);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_ansatz(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, const double* theta, int full_unitary,
+                void* out, int dtype, void* stream) {
+  if (!ops || nops < 0 || nq < 1 || nq > 5 || N < 0 || (!theta && N && P) || (!out && N))
+    return fail(QMPS_ERR_ARG, "ansatz: bad arguments (nq must be 1..5)");
+  for (int k = 0; k < nops; ++k)
+    if (ops[k].param >= P || ops[k].q0 < 0 || ops[k].q0 >= nq || ops[k].q1 < 0 || ops[k].q1 >= nq)
+      return fail(QMPS_ERR_ARG, "ansatz: gate references a parameter or qubit out of range");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GateOp* dops = nullptr;
+  if (int rc = to_device_async((const GateOp*)ops, (size_t)nops, &dops, st)) return rc;
+  int rc = dtype == QMPS_C128 ? ansatz_f64(dops, nops, nq, N, P, theta, full_unitary, out, st)
+                              : ansatz_f32(dops, nops, nq, N, P, theta, full_unitary, out, st);
+  if (dops) CK(cudaFreeAsync(dops, st));
+  return rc;
+}
+
+int qmps_energy_theta(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, const double* theta,
+                      const void* hmat, int coord, const double* shifts, int nshift, void* energy,
+                      int32_t* status, int dtype, void* stream) {
+  if (!ops || nops < 1 || nq < 2 || nq > 5 || N < 0 || !theta || !hmat || !energy || nshift < 0 || (nshift && !shifts))
+    return fail(QMPS_ERR_ARG, "energy_theta: bad arguments (nq must be 2..5)");
+  if (nshift && (coord < 0 || coord >= P)) return fail(QMPS_ERR_ARG, "energy_theta: coord out of range");
+  for (int k = 0; k < nops; ++k)
+    if (ops[k].param >= P || ops[k].q0 < 0 || ops[k].q0 >= nq || ops[k].q1 < 0 || ops[k].q1 >= nq)
+      return fail(QMPS_ERR_ARG, "energy_theta: gate references a parameter or qubit out of range");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GateOp* dops = nullptr;
+  double* dsh = nullptr;
+  if (int rc = to_device_async((const GateOp*)ops, (size_t)nops, &dops, st)) return rc;
+  if (int rc = to_device_async(shifts, (size_t)nshift, &dsh, st)) return rc;
+  int rc = 0;
+  const int D = 1 << (nq - 1);
+  if (D == 2 && nops <= d2_max_ops()) {
+    rc = energy_d2_theta(dops, nops, N, P, theta, hmat, coord, dsh, nshift, energy, status, dtype, st);
+  } else {
+    EnvParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = 2; p.D = D; p.N = N; p.assume_lc = 1; p.status = status;
+    p.ops = dops; p.nops = nops; p.nq = nq; p.P = P; p.theta = theta; p.coord = coord; p.shifts = dsh; p.nshift = nshift;
+    p.hmat = hmat; p.energy = energy; p.two_site = 0;
+    rc = dtype == QMPS_C128 ? env_generic_f64(p, 1, st) : env_generic_f32(p, 1, st);
+  }
+  if (!rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(QMPS_ERR_CUDA, cudaGetErrorString(e)); }
+  if (dops) cudaFreeAsync(dops, st);
+  if (dsh) cudaFreeAsync(dsh, st);
+  return rc;
+}
+
+int qmps_energy_tensor(int D, int64_t N, const void* in, int two_site, const void* hmat, void* energy,
+                       int32_t* status, int dtype, void* stream) {
+  if (N < 0 || (!in && N) || !hmat || (!energy && N)) return fail(QMPS_ERR_ARG, "energy_tensor: bad arguments");
+  if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "energy_tensor: D must be 1, 2, 4, 8 or 16");
+  if (N == 0) return 0;
+  EnvParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = two_site ? 4 : 2; p.D = D; p.N = N; p.in = in; p.assume_lc = 1; p.status = status; p.coord = -1;
+  p.hmat = hmat; p.energy = energy; p.two_site = two_site;
+  return dtype == QMPS_C128 ? env_generic_f64(p, 1, (cudaStream_t)stream) : env_generic_f32(p, 1, (cudaStream_t)stream);
+}
+
+int qmps_rotosolve_fit(int64_t N, int nshift, const double* cost, double* theta_star, double* fit, double* theta_io,
+                       int P, int coord, void* stream) {
+  if (N < 0 || (nshift != 3 && nshift != 6) || (!cost && N)) return fail(QMPS_ERR_ARG, "rotosolve_fit: nshift must be 3 or 6");
+  if (theta_io && (coord < 0 || coord >= P)) return fail(QMPS_ERR_ARG, "rotosolve_fit: coord out of range");
+  if (N == 0) return 0;
+  const int grid = (int)((N + 127) / 128 < (int64_t)sm_count() * 8 ? (N + 127) / 128 : (int64_t)sm_count() * 8);
+  rotosolve_fit_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(N, nshift, cost, theta_star, fit, theta_io, P, coord);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh,
+                  int dtype, void* stream) {
+  if (d < 1 || D < 1 || N < 0 || K < 0 || (N && (!A || !B || !r_io))) return fail(QMPS_ERR_ARG, "tm_power: bad arguments");
+  if (N * d > 65535) return fail(QMPS_ERR_UNSUPPORTED, "tm_power: N*d > 65535 (split the batch)");
+  if (dtype == QMPS_C128) return tm_power_impl<double>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
+  if (dtype == QMPS_C64) return tm_power_impl<float>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
+  return fail(QMPS_ERR_ARG, "tm_power: bad dtype");
+}
+
+int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* best_cost, int64_t* best_index,
+                void* stream) {
+  if (N < 0 || (!cost && N) || !best_cost || !best_index) return fail(QMPS_ERR_ARG, "argmin: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)((N + 255) / 256);
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+  if (grid < 1) grid = 1;
+  double* bc = nullptr; int64_t* bi = nullptr; unsigned int* ctr = nullptr;
+  CK(cudaMallocAsync((void**)&bc, sizeof(double) * grid, st));
+  CK(cudaMallocAsync((void**)&bi, sizeof(int64_t) * grid, st));
+  CK(cudaMallocAsync((void**)&ctr, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+  argmin_kernel<<<grid, 256, 0, st>>>(N, cost, index_offset, bc, bi, ctr, best_cost, best_index);
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(bc, st));
+  CK(cudaFreeAsync(bi, st));
+  CK(cudaFreeAsync(ctr, st));
+  return 0;
+}
+
+int qmps_loschmidt_rate(int64_t NT, const double* t, double g0, double g1, double* out, void* stream) {
+  if (NT < 0 || (NT && (!t || !out))) return fail(QMPS_ERR_ARG, "loschmidt_rate: bad arguments");
+  if (NT == 0) return 0;
+  int grid = (int)((NT + 3) / 4);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  loschmidt_rate_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(NT, t, g0, g1, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- host-buffer pipeline: chunked H2D -> solve -> D2H on rotating streams ---------------------
+int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_U, int assume_left_canonical,
+                        void* eta, void* r, void* C, int32_t* status, int dtype, int device) {
+  if (N < 0 || (!in && N)) return fail(QMPS_ERR_ARG, "env_exact_host: bad arguments");
+  if (!is_pow2(D) || D > 16 || d < 1 || d > 4) return fail(QMPS_ERR_UNSUPPORTED, "env_exact_host: unsupported d/D");
+  if (in_is_full_U && d != 2) return fail(QMPS_ERR_ARG, "env_exact_host: unitary input implies d = 2");
+  if (N == 0) return 0;
+  CK(cudaSetDevice(device));
+  const size_t csz = dtype == QMPS_C128 ? 16 : 8;
+  const size_t in_per = csz * (in_is_full_U ? (size_t)4 * D * D : (size_t)d * D * D);
+  const size_t mat_per = csz * (size_t)D * D;
+  const size_t out_per = (eta ? csz : 0) + (r ? mat_per : 0) + (C ? mat_per : 0) + (status ? 4 : 0);
+  // chunk so that one chunk moves ~16 MiB in; at least 3 chunks in flight for overlap
+  int64_t chunk = (int64_t)((16u << 20) / in_per);
+  if (chunk < 1) chunk = 1;
+  if (chunk > N) chunk = N;
+  const int NS = 3;
+  struct Slot { cudaStream_t st; char* din; char* dout; };
+  static std::mutex mu;
+  static Slot slots[64][NS];
+  static size_t cap_in[64] = {0}, cap_out[64] = {0};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return fail(QMPS_ERR_ARG, "env_exact_host: bad device");
+  Slot* sl = slots[device];
+  const size_t need_in = (size_t)chunk * in_per, need_out = (size_t)chunk * (out_per ? out_per : 1);
+  if (cap_in[device] < need_in || cap_out[device] < need_out) {
+    for (int k = 0; k < NS; ++k) {
+      if (sl[k].din) cudaFree(sl[k].din);
+      if (sl[k].dout) cudaFree(sl[k].dout);
+      if (!sl[k].st) CK(cudaStreamCreateWithFlags(&sl[k].st, cudaStreamNonBlocking));
+      CK(cudaMalloc((void**)&sl[k].din, need_in));
+      CK(cudaMalloc((void**)&sl[k].dout, need_out));
+    }
+    cap_in[device] = need_in; cap_out[device] = need_out;
+  }
+  int rc = 0;
+  int k = 0;
+  for (int64_t off = 0; off < N && !rc; off += chunk, k = (k + 1) % NS) {
+    const int64_t cnt = (N - off < chunk) ? (N - off) : chunk;
+    Slot& s = sl[k];
+    CK(cudaMemcpyAsync(s.din, (const char*)in + (size_t)off * in_per, (size_t)cnt * in_per, cudaMemcpyHostToDevice, s.st));
+    char* o = s.dout;
+    char* d_eta = nullptr; char* d_r = nullptr; char* d_C = nullptr; char* d_st = nullptr;
+    if (eta) { d_eta = o; o += (size_t)cnt * csz; }
+    if (r) { d_r = o; o += (size_t)cnt * mat_per; }
+    if (C) { d_C = o; o += (size_t)cnt * mat_per; }
+    if (status) { d_st = o; }
+    rc = env_exact_any(d, D, cnt, s.din, in_is_full_U, assume_left_canonical, d_eta, d_r, d_C, (int32_t*)d_st, dtype, s.st);
+    if (rc) break;
+    if (eta) CK(cudaMemcpyAsync((char*)eta + (size_t)off * csz, d_eta, (size_t)cnt * csz, cudaMemcpyDeviceToHost, s.st));
+    if (r) CK(cudaMemcpyAsync((char*)r + (size_t)off * mat_per, d_r, (size_t)cnt * mat_per, cudaMemcpyDeviceToHost, s.st));
+    if (C) CK(cudaMemcpyAsync((char*)C + (size_t)off * mat_per, d_C, (size_t)cnt * mat_per, cudaMemcpyDeviceToHost, s.st));
+    if (status) CK(cudaMemcpyAsync((char*)status + (size_t)off * 4, d_st, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.st));
+  }
+  for (int q = 0; q < NS; ++q) if (sl[q].st) CK(cudaStreamSynchronize(sl[q].st));
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// qmps_b200: generic-D launchers, REAL = float instantiation (own translation unit so
+// the two precisions compile in parallel).
+#include "api_common.cuh"
+
+using namespace qmps;
+namespace qmps_host {
+namespace {
+typedef float REAL;
+
+template <int G, int MODE>
+int launch_env_generic(EnvParams p, cudaStream_t st) {
+  const int n = p.D * p.D;
+  const int e_in_smem = n <= 64;
+  const int block = G > 32 ? G : 128;
+  const int gpc = G > 32 ? 1 : block / G;
+  const EnvLayout<REAL> L = env_layout<REAL>(p.d, p.D, p.nops, G > 32 ? block : G, e_in_smem, (MODE == 1) || !p.assume_lc);
+  const size_t smem = L.total * gpc;
+  auto kern = env_generic_kernel<REAL, G, MODE>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  const int S = (MODE == 1 && p.nshift > 0) ? p.nshift : 1;
+  const int64_t total = p.N * S;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (total + gpc - 1) / gpc, &grid)) return rc;
+  void* ws = nullptr;
+  if (!e_in_smem) {
+    p.ws_stride = (size_t)n * (n + 1);
+    CK(cudaMallocAsync(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
+    p.ws = ws;
+  } else {
+    p.ws = nullptr; p.ws_stride = 0;
+  }
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  if (ws) CK(cudaFreeAsync(ws, st));
+  return 0;
+}
+
+template <int MODE> int dispatch_env(const EnvParams& p, cudaStream_t st) {
+  switch (group_for_n(p.D * p.D)) {
+    case 4: return launch_env_generic<4, MODE>(p, st);
+    case 16: return launch_env_generic<16, MODE>(p, st);
+    case 128: return launch_env_generic<128, MODE>(p, st);
+    default: return launch_env_generic<256, MODE>(p, st);
+  }
+}
+
+template <int G> int launch_fp(FpParams p, cudaStream_t st) {
+  const int n = p.D * p.D;
+  const int h_in_smem = n <= 64;
+  const int block = G > 32 ? G : 128;
+  const int gpc = G > 32 ? 1 : block / G;
+  const FpLayout<REAL> L = fp_layout<REAL>(p.D, h_in_smem);
+  const size_t smem = L.total * gpc;
+  auto kern = fixed_point_kernel<REAL, G>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
+  void* ws = nullptr;
+  if (!h_in_smem) {
+    p.ws_stride = (size_t)n * (n + 1);
+    CK(cudaMallocAsync(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
+    p.ws = ws;
+  } else { p.ws = nullptr; p.ws_stride = 0; }
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  if (ws) CK(cudaFreeAsync(ws, st));
+  return 0;
+}
+
+template <int G>
+int launch_ansatz(const GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out,
+                  cudaStream_t st) {
+  const int R = 1 << nq, nc = full ? R : R / 2;
+  const size_t per = (((size_t)R * nc * sizeof(cx<REAL>) + 15) & ~size_t(15)) + (((size_t)2 * nops * sizeof(REAL) + 15) & ~size_t(15));
+  const int block = G > 32 ? G : 128;
+  const int gpc = G > 32 ? 1 : block / G;
+  const size_t smem = per * gpc;
+  auto kern = ansatz_kernel<REAL, G>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (N + gpc - 1) / gpc, &grid)) return rc;
+  kern<<<grid, block, smem, st>>>(dops, nops, nq, N, P, theta, full, (cx<REAL>*)out);
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+int env_generic_f32(const EnvParams& p, int mode, cudaStream_t st) {
+  return mode == 0 ? dispatch_env<0>(p, st) : dispatch_env<1>(p, st);
+}
+int fixed_point_f32(const FpParams& p, cudaStream_t st) {
+  switch (group_for_n(p.D * p.D)) {
+    case 4: return launch_fp<4>(p, st);
+    case 16: return launch_fp<16>(p, st);
+    case 128: return launch_fp<128>(p, st);
+    default: return launch_fp<256>(p, st);
+  }
+}
+int ansatz_f32(const GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out,
+               cudaStream_t st) {
+  const int R = 1 << nq, elems = R * (full ? R : R / 2);
+  return elems <= 8 ? launch_ansatz<4>(dops, nops, nq, N, P, theta, full, out, st)
+       : elems <= 64 ? launch_ansatz<16>(dops, nops, nq, N, P, theta, full, out, st)
+                     : launch_ansatz<32>(dops, nops, nq, N, P, theta, full, out, st);
+}
+}  // namespace qmps_host

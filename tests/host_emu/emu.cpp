@@ -1,0 +1,144 @@
+// TEST INFRASTRUCTURE ONLY: compiles the product's device algorithms
+// (qmps_b200/csrc/*.cuh, which are __host__ __device__ templates) as plain C++ with a
+// cooperating group of ONE lane, so their arithmetic can be checked against the
+// oracle on a machine without a GPU.  This library is never loaded by qmps_b200.
+#include <stdint.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../qmps_b200/csrc/core.cuh"
+#include "../../qmps_b200/csrc/ansatz.cuh"
+#include "../../qmps_b200/csrc/generic.cuh"
+#include "../../qmps_b200/csrc/d2.cuh"
+
+using namespace qmps;
+typedef cx<double> zc;
+
+static Grp solo() { Grp g; g.lane = 0; g.size = 1; g.mask = 1; g.cta = 0; return g; }
+
+extern "C" {
+
+int emu_env_d2(int64_t N, const double* a, double* r, double* eta, double* C, int32_t* status) {
+  for (int64_t n = 0; n < N; ++n) {
+    double e;
+    status[n] = env_d2_solve<double, true>((const zc*)a + n * 8, (zc*)r + n * 4, &e, (zc*)C + n * 4);
+    eta[2 * n] = e; eta[2 * n + 1] = 0;
+  }
+  return 0;
+}
+
+int emu_env_generic(int d, int D, int64_t N, const double* A, int assume_lc, double* eta, double* r, double* C,
+                    int32_t* status) {
+  const int n = D * D, ld = n + 1;
+  std::vector<zc> E((size_t)n * ld), x(n), Cc(n), w(n), vv(n), rc(n), rs(n);
+  std::vector<double> rn(n), red(1);
+  std::vector<int> step(n), done(n);
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p) {
+    const zc* a = (const zc*)A + p * (size_t)d * n;
+    int st;
+    zc lam = mk<double>(1, 0);
+    if (assume_lc) {
+      double er;
+      st = env_solve_direct<double>(g, a, d, D, E.data(), ld, x.data(), step.data(), done.data(), red.data(), &er);
+      lam = mk<double>(er, 0);
+    } else {
+      st = leading_eigenpair<double>(g, a, a, d, D, 0, 1, E.data(), ld, w.data(), vv.data(), rc.data(), rs.data(),
+                                     rn.data(), x.data(), step.data(), done.data(), &lam);
+      hermitise<double>(g, x.data(), D);
+      double tr = 0;
+      for (int i = 0; i < D; ++i) tr += x[i * D + i].re;
+      for (int e = 0; e < n; ++e) x[e] = x[e] * (1.0 / tr);
+    }
+    int bad = cholesky_lower<double>(g, x.data(), D, Cc.data(), D, D);
+    if (bad && st == ST_OK) st = ST_NOT_PD;
+    status[p] = st;
+    eta[2 * p] = lam.re; eta[2 * p + 1] = lam.im;
+    for (int e = 0; e < n; ++e) { ((zc*)r)[p * n + e] = x[e]; ((zc*)C)[p * n + e] = Cc[e]; }
+  }
+  return 0;
+}
+
+int emu_fixed_point(int d, int D, int64_t N, const double* A, const double* B, int left, double* eta, double* vec,
+                    int32_t* status) {
+  const int n = D * D, ld = n + 1;
+  std::vector<zc> H((size_t)n * ld), x(n), w(n), vv(n), rc(n), rs(n);
+  std::vector<double> rn(n);
+  std::vector<int> step(n), done(n);
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p) {
+    zc lam;
+    status[p] = leading_eigenpair<double>(g, (const zc*)A + p * (size_t)d * n, (const zc*)B + p * (size_t)d * n, d, D,
+                                          left, 1, H.data(), ld, w.data(), vv.data(), rc.data(), rs.data(), rn.data(),
+                                          x.data(), step.data(), done.data(), &lam);
+    eta[2 * p] = lam.re; eta[2 * p + 1] = lam.im;
+    for (int e = 0; e < n; ++e) ((zc*)vec)[p * n + e] = x[e];
+  }
+  return 0;
+}
+
+// all eigenvalues of a dense n x n matrix (row-major, interleaved complex)
+int emu_eigvals(int n, const double* M, double* w_out) {
+  const int ld = n + 1;
+  std::vector<zc> H((size_t)n * ld), w(n), vv(n), rc(n), rs(n);
+  std::vector<double> rn(n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) H[i * ld + j] = ((const zc*)M)[i * n + j];
+  Grp g = solo();
+  hessenberg<double>(g, H.data(), ld, n, vv.data());
+  int fail = hqr_eigenvalues<double>(g, H.data(), ld, n, w.data(), rc.data(), rs.data(), rn.data());
+  for (int i = 0; i < n; ++i) { w_out[2 * i] = w[i].re; w_out[2 * i + 1] = w[i].im; }
+  return fail;
+}
+
+int emu_ansatz(const GateOp* ops, int nops, int nq, int64_t N, int P, const double* theta, int full, int coord,
+               double shift, double* out) {
+  const int R = 1 << nq, nc = full ? R : R / 2;
+  std::vector<double> trig(2 * (nops > 0 ? nops : 1));
+  StateLayout SL; SL.R = R; SL.ncols = nc; SL.a_layout = full ? 0 : 1;
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p)
+    ansatz_eval<double>(g, ops, nops, theta + p * P, coord, shift, nq, SL, (zc*)out + p * (size_t)R * nc, trig.data());
+  return 0;
+}
+
+// two-qubit register path: out = A[2][2][2] per problem
+int emu_ansatz_reg2(const GateOp* ops, int nops, int64_t N, int P, const double* theta, int coord, double shift,
+                    double* out) {
+  for (int64_t p = 0; p < N; ++p) {
+    zc x[8];
+    ansatz_reg2<double, 2>(ops, nops, theta + p * P, coord, shift, x);
+    zc* a = (zc*)out + p * 8;
+    for (int row = 0; row < 4; ++row) for (int j = 0; j < 2; ++j) a[(row & 1) * 4 + (row >> 1) * 2 + j] = x[row * 2 + j];
+  }
+  return 0;
+}
+
+int emu_energy_d2(int64_t N, const double* a, const double* hmat, double* energy) {
+  for (int64_t n = 0; n < N; ++n) {
+    zc r[4], C[4];
+    double eta;
+    env_d2_solve<double, true>((const zc*)a + n * 8, r, &eta, C);
+    energy[n] = energy_d2<double>((const zc*)a + n * 8, r, (const zc*)hmat);
+  }
+  return 0;
+}
+
+// in: A [N][2][D][D] (two_site = 0) or M [N][4][D][D] (two_site = 1)
+int emu_energy_generic(int D, int64_t N, const double* in, int two_site, const double* hmat, double* energy) {
+  const int n = D * D, ld = n + 1, d = two_site ? 4 : 2;
+  std::vector<zc> E((size_t)n * ld), x(n), tmp(8 * n);
+  std::vector<double> red(1);
+  std::vector<int> step(n), done(n);
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p) {
+    const zc* a = (const zc*)in + p * (size_t)d * n;
+    double er;
+    env_solve_direct<double>(g, a, d, D, E.data(), ld, x.data(), step.data(), done.data(), red.data(), &er);
+    const zc* M = a;
+    if (!two_site) { merge_block<double>(g, a, a, 2, 2, D, tmp.data()); M = tmp.data(); }
+    energy[p] = energy_from_block<double>(g, M, x.data(), D, (const zc*)hmat, tmp.data() + 4 * n, red.data());
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,487 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same
+seeded inputs, plus size-independent properties at full size.  Tolerances follow the
+north star: 1e-10 relative in complex128, 1e-5 in complex64 (gap-aware where the
+problem's condition number enters)."""
+import numpy as np
+import pytest
+from scipy.stats import unitary_group
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from qmps_b200 import batched, represent, _lib
+    _lib.require_device()
+    import oracle as O
+    return dict(torch=torch, B=batched, R=represent, O=O, L=_lib)
+
+
+def haar_batch(n, count, seed):
+    return np.stack([unitary_group.rvs(n, random_state=seed + k) for k in range(count)])
+
+
+def tensors(D, count, seed, O):
+    return np.ascontiguousarray(np.stack([O.unitary_to_tensor(u) for u in haar_batch(2 * D, count, seed)]))
+
+
+def gap_of(A, O):
+    w = np.sort(np.abs(np.linalg.eigvals(O.transfer_matrix(A))))[::-1]
+    return 1.0 - w[1]
+
+
+# ---------------------------------------------------------------- a4/a5, D = 2 fast path
+@pytest.mark.parametrize("form", ["A", "U"])
+@pytest.mark.parametrize("want_C", [True, False])
+def test_env_d2_vs_oracle(env, form, want_C):
+    t, B, O = env["torch"], env["B"], env["O"]
+    N = 1000                                     # not a multiple of 32: ragged last tile
+    U = haar_batch(4, N, 10)
+    A = np.stack([O.unitary_to_tensor(u) for u in U])
+    res = B.env_exact(A=t.from_numpy(A).cuda(), want_C=want_C) if form == "A" else B.env_exact(U=t.from_numpy(U).cuda(), want_C=want_C)
+    eta, r = res.eta.cpu().numpy(), res.r.cpu().numpy()
+    assert int(res.status.abs().sum()) == 0
+    for k in range(N):
+        e0, r0, C0, _ = O.env_exact_parts(A[k])
+        tol = TOL / min(1.0, gap_of(A[k], O))
+        assert abs(eta[k] - e0) < TOL
+        assert np.abs(r[k] - r0).max() < tol
+        if want_C:
+            assert np.abs(res.C[k].cpu().numpy() - C0).max() < 10 * tol / np.sqrt(np.linalg.eigvalsh(r0)[0])
+
+
+def test_env_d2_full_size_properties(env):
+    """2^20 problems (BASELINE config 2): fixed-point equation, trace, hermiticity, r = C C^dagger."""
+    t, B = env["torch"], env["B"]
+    N = 1 << 20
+    g = t.Generator(device="cuda").manual_seed(1)
+    Z = t.randn((N, 4, 2), dtype=t.float64, device="cuda", generator=g) + 1j * t.randn((N, 4, 2), dtype=t.float64, device="cuda", generator=g)
+    Q, _ = t.linalg.qr(Z)                                    # iso[(i,s), j], columns orthonormal
+    A = Q.reshape(N, 2, 2, 2).permute(0, 2, 1, 3).contiguous()   # A[s,i,j] = iso[2i+s, j]
+    res = B.env_exact(A=A)
+    r, C, eta = res.r, res.C, res.eta
+    ok = res.status == 0
+    assert ok.float().mean() > 0.999
+    phi = t.einsum("nsij,njl,nskl->nik", A, r, A.conj())
+    gap_scale = 1e-9
+    assert (phi - r)[ok].abs().max() < gap_scale
+    assert (t.einsum("nii->n", r).real - 1).abs().max() < 1e-12
+    assert (r - r.conj().transpose(1, 2)).abs().max() == 0
+    assert (eta[ok] - 1).abs().max() < 1e-12
+    assert (C @ C.conj().transpose(1, 2) - r)[ok].abs().max() < 1e-12
+    assert C[:, 0, 1].abs().max() == 0 and (C[:, 0, 0].imag.abs().max() == 0)
+
+
+def test_env_d2_not_positive_definite_is_flagged(env):
+    """Product state: r has rank one, the reference's cholesky raises LinAlgError (tools.py:182)."""
+    t, B, L = env["torch"], env["B"], env["L"]
+    U = np.eye(4, dtype=np.complex128)[None]
+    res = B.env_exact(U=t.from_numpy(U).cuda())
+    assert int(res.status[0]) == L.ST_NOT_PD
+    from qmps_b200 import tools
+    with pytest.raises(np.linalg.LinAlgError):
+        tools.get_env_exact(U[0])
+
+
+def test_env_empty_and_single(env):
+    t, B = env["torch"], env["B"]
+    res = B.env_exact(A=t.zeros((0, 2, 2, 2), dtype=t.complex128, device="cuda"))
+    assert res.r.shape == (0, 2, 2)
+    A = tensors(2, 1, 5, env["O"])
+    res = B.env_exact(A=t.from_numpy(A).cuda())
+    _, r0, _, _ = env["O"].env_exact_parts(A[0])
+    assert np.abs(res.r[0].cpu().numpy() - r0).max() < TOL
+
+
+def test_env_d2_complex64(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(2, 256, 77, O)
+    res = B.env_exact(A=t.from_numpy(A).cuda().to(t.complex64))
+    for k in range(256):
+        _, r0, C0, _ = O.env_exact_parts(A[k])
+        assert np.abs(res.r[k].cpu().numpy() - r0).max() < 1e-5 / min(1.0, gap_of(A[k], O))
+
+
+# ---------------------------------------------------------------- a4/a5 generic D
+@pytest.mark.parametrize("D,count", [(2, 64), (4, 64), (8, 24), (16, 3)])
+@pytest.mark.parametrize("lc", [True, False])
+def test_env_generic_vs_oracle(env, D, count, lc):
+    t, B, O = env["torch"], env["B"], env["O"]
+    if D == 2 and lc:
+        pytest.skip("covered by the fast path tests")
+    if D == 16 and not lc:
+        count = 1
+    A = tensors(D, count, 200 + D, O)
+    res = B.env_exact(A=t.from_numpy(A).cuda(), assume_left_canonical=lc)
+    assert int(res.status.abs().sum()) == 0
+    for k in range(count):
+        e0, r0, C0, _ = O.env_exact_parts(A[k])
+        tol = 10 * TOL / min(1.0, gap_of(A[k], O))
+        assert abs(res.eta[k].cpu().numpy() - e0) < 1e-9
+        assert np.abs(res.r[k].cpu().numpy() - r0).max() < tol
+        assert np.abs(res.C[k].cpu().numpy() - C0).max() < 100 * tol
+
+
+def test_env_general_tensor_not_canonical(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    rng = np.random.default_rng(4)
+    A = rng.normal(size=(32, 2, 4, 4)) + 1j * rng.normal(size=(32, 2, 4, 4))
+    res = B.env_exact(A=t.from_numpy(A).cuda(), assume_left_canonical=False, want_C=False)
+    for k in range(32):
+        e0, _, r0 = O.eigs(A[k])
+        assert abs(res.eta[k].cpu().numpy() - e0) < 1e-9 * abs(e0)
+        assert np.abs(res.r[k].cpu().numpy() - r0).max() < 1e-9
+
+
+def test_env_two_site_block(env):
+    """d = 4 input (merge(A1, A2)) as used by NonSparseFullTwoSiteEnergyOptimizer.env_function."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(2, 32, 31, O)
+    M = np.stack([O.merge(A[k], A[(k + 1) % 32]) for k in range(32)])
+    res = B.env_exact(A=t.from_numpy(M).cuda())
+    for k in range(32):
+        _, r0, C0, _ = O.env_exact_parts(M[k])
+        assert np.abs(res.r[k].cpu().numpy() - r0).max() < 1e-9
+
+
+# ---------------------------------------------------------------- a6/a8/a11 mixed fixed points
+@pytest.mark.parametrize("D,count", [(2, 128), (4, 48), (8, 6)])
+@pytest.mark.parametrize("left", [False, True])
+def test_fixed_point_vs_oracle(env, D, count, left):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A, Bt = tensors(D, count, 300 + D, O), tensors(D, count, 900 + D, O)
+    fp = B.fixed_point(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), left=left)
+    assert int(fp.status.abs().sum()) == 0
+    eta, vec = fp.eta.cpu().numpy(), fp.vec.cpu().numpy()
+    for k in range(count):
+        x0, v0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])
+        E = O.transfer_matrix(A[k], Bt[k])
+        Em = E.conj().T if left else E
+        w = np.sort(np.abs(np.linalg.eigvals(E)))[::-1]
+        gap = max(w[0] - w[1], 1e-3)
+        assert abs(abs(eta[k]) - abs(x0)) < TOL * 10
+        assert abs(fp.fid[k].item() - abs(x0) ** 2) < TOL * 10
+        assert abs(fp.cost[k].item() + np.sqrt(abs(x0))) < TOL * 10
+        assert abs(fp.echo[k].item() + np.log(abs(x0) ** 2)) < TOL * 100
+        v = vec[k].reshape(-1)
+        assert abs(np.linalg.norm(v) - 1) < 1e-12
+        assert np.abs(Em @ v - eta[k] * v).max() < 1e-11 / gap
+        if abs(eta[k] - x0) < 1e-9:                 # same eigenvalue picked: same gauge-fixed vector
+            assert np.abs(vec[k] - v0).max() < 1e-9 / gap
+
+
+def test_fixed_point_outer_and_broadcast(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A, Bt = tensors(2, 3, 1, O), tensors(2, 5, 2, O)
+    fp = B.fixed_point(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), pair="outer")
+    assert fp.eta.shape == (3, 5)
+    for i in range(3):
+        for j in range(5):
+            assert abs(abs(fp.eta[i, j].item()) - abs(O.right_fixed_point(A[i], Bt[j])[0])) < TOL * 10
+    fp = B.fixed_point(t.from_numpy(A[:1]).cuda(), t.from_numpy(Bt).cuda())
+    for j in range(5):
+        assert abs(abs(fp.eta[j].item()) - abs(O.right_fixed_point(A[0], Bt[j])[0])) < TOL * 10
+
+
+def test_self_overlap_is_one(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(4, 16, 3, O)
+    fp = B.fixed_point(t.from_numpy(A).cuda(), t.from_numpy(A).cuda())
+    assert (fp.fid - 1).abs().max() < 1e-12
+
+
+# ---------------------------------------------------------------- a1/a2/a3/a7
+def test_unitary_to_tensor_and_back(env, golden):
+    t, B = env["torch"], env["B"]
+    g = golden["ref_tools"]
+    for D in (2, 4, 8):
+        U, Aref = g[f"u2t_U_D{D}"], g[f"u2t_A_D{D}"]
+        A = B.unitary_to_tensor(t.from_numpy(U).cuda())
+        assert np.array_equal(A.cpu().numpy(), Aref)          # pure index shuffle: bit exact
+        U2 = B.tensor_to_unitary(A).cpu().numpy()
+        n = 2 * D
+        for k in range(len(U)):
+            assert np.array_equal(U2[k][:, :D], g[f"t2u_U_D{D}"][k][:, :D])   # unique columns, exact
+            assert np.abs(U2[k].conj().T @ U2[k] - np.eye(n)).max() < 1e-13
+            assert np.array_equal(B.unitary_to_tensor(t.from_numpy(U2[k:k + 1]).cuda()).cpu().numpy()[0], Aref[k])
+
+
+def test_environment_to_unitary(env, golden):
+    t, B = env["torch"], env["B"]
+    g = golden["ref_tools"]
+    for key in ("e2u_in", "e2u_in_D4"):
+        C = g[key]
+        V = B.environment_to_unitary(t.from_numpy(C.reshape(1, -1)).cuda()).cpu().numpy()[0]
+        ref = g[key.replace("in", "out")]
+        n = V.shape[0]
+        assert np.abs(V[:, 0] - ref[:, 0]).max() < 1e-15       # the unique column
+        assert np.abs(V.conj().T @ V - np.eye(n)).max() < 1e-13
+
+
+def test_merge(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    for D in (2, 4, 8):
+        A, Bt = tensors(D, 6, 40 + D, O), tensors(D, 6, 60 + D, O)
+        M = B.merge(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()).cpu().numpy()
+        for k in range(6):
+            assert np.abs(M[k] - O.merge(A[k], Bt[k])).max() < 1e-14
+    W = np.stack([O.tfim_evolution_gate(0.2, 0.1 * k) for k in range(5)])
+    A = tensors(2, 1, 9, O)
+    M = B.merge(t.from_numpy(A).cuda(), t.from_numpy(A).cuda(), t.from_numpy(W).cuda()).cpu().numpy()
+    for k in range(5):
+        assert np.abs(M[k] - O.apply_two_site_gate(W[k], O.merge(A[0], A[0]))).max() < 1e-14
+
+
+# ---------------------------------------------------------------- a14 ansaetze
+def ansatz_cases(R, O, rng):
+    return [
+        (R.ShallowFullStateTensor(2, rng.normal(size=15)), O.shallow_full_state_tensor),
+        (R.ShallowCNOTStateTensor(2, rng.normal(size=4)), lambda p: O.shallow_cnot_state_tensor(2, p)),
+        (R.ShallowCNOTStateTensor(8, rng.normal(size=6)), lambda p: O.shallow_cnot_state_tensor(8, p)),
+        (R.ShallowCNOTStateTensor_nonuniform(4, rng.normal(size=12)), lambda p: O.shallow_cnot_state_tensor_nonuniform(4, p)),
+        (R.ShallowCNOTStateTensor_nonuniform(8, rng.normal(size=24)), lambda p: O.shallow_cnot_state_tensor_nonuniform(8, p)),
+        (R.ShallowCNOTStateTensor_nonuniform(16, rng.normal(size=10)), lambda p: O.shallow_cnot_state_tensor_nonuniform(16, p)),
+        (R.ShallowCNOTStateTensor3(4, rng.normal(size=6)), lambda p: O.shallow_cnot_state_tensor3(4, p)),
+        (R.ShallowQAOAStateTensor(4, rng.normal(size=6)), lambda p: O.shallow_qaoa_state_tensor(4, p)),
+        (R.ExactAfter4(2, rng.normal(size=12)), lambda p: O.exact_after4(2, p)),
+        (R.ExactAfter4(4, rng.normal(size=12)), lambda p: O.exact_after4(4, p)),
+        (R.StateGate(rng.normal(size=6)), O.state_gate),
+        (R.GSFAnsatz(rng.normal(size=8)), O.gsf_ansatz),
+    ]
+
+
+def test_ansatz_families(env):
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    rng = np.random.default_rng(3)
+    for gate, ofn in ansatz_cases(R, O, rng):
+        theta = rng.normal(size=(5, gate.p))
+        U = B.ansatz_tensors(gate.program(), theta, full_unitary=True).cpu().numpy()
+        A = B.ansatz_tensors(gate.program(), theta).cpu().numpy()
+        for k in range(5):
+            Uo = ofn(theta[k])
+            assert np.abs(U[k] - Uo).max() < 1e-13, type(gate).__name__
+            assert np.abs(A[k] - O.unitary_to_tensor(Uo)).max() < 1e-13
+        assert np.abs(R.unitary(gate) - ofn(gate.params)).max() < 1e-13
+
+
+# ---------------------------------------------------------------- a9/a12 energies and rotosolve
+@pytest.mark.parametrize("D,layers,count", [(2, 3, 64), (4, 2, 32), (8, 3, 8)])
+def test_energy_theta_with_shifts(env, D, layers, count):
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    nq = int(np.log2(D)) + 1
+    rng = np.random.default_rng(50 + D)
+    theta = rng.normal(size=(count, 2 * nq * layers))
+    gate = R.ShallowCNOTStateTensor_nonuniform(D, theta[0])
+    H = O.heisenberg_matrix() if D == 8 else O.tfim_matrix(1.0)
+    coord = 3
+    for shifts in (None, B.ROTO3_SHIFTS, B.ROTO6_SHIFTS):
+        e = B.energy_theta(gate.program(), theta, H, coord=coord if shifts else None, shifts=shifts).cpu().numpy()
+        for n in range(min(count, 6)):
+            for s, sh in enumerate(shifts or (0.0,)):
+                th = theta[n].copy(); th[coord] += sh
+                ref = O.energy_transfer(O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(D, th)), H)
+                got = e[n, s] if shifts else e[n]
+                assert abs(got - ref) < 1e-9, (D, n, s, got, ref)
+
+
+def test_energy_sfst_matches_statevector_route(env):
+    """Against the reference's own route: get_env_exact -> State(U,V,2) -> simulate (ground_state.py:251-266)."""
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    rng = np.random.default_rng(8)
+    theta = rng.normal(size=(16, 15))
+    H = O.tfim_matrix(0.7)
+    e = B.energy_theta(R.ShallowFullStateTensor(2, theta[0]).program(), theta, H).cpu().numpy()
+    for n in range(16):
+        assert abs(e[n] - O.energy_of_unitary(O.shallow_full_state_tensor(theta[n]), H)) < 1e-9
+
+
+def test_energy_tensor_and_two_site(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    H = O.tfim_matrix(1.3)
+    for D in (2, 4, 8):
+        A = tensors(D, 8, 70 + D, O)
+        e = B.energy_tensor(t.from_numpy(A).cuda(), H).cpu().numpy()
+        for k in range(8):
+            assert abs(e[k] - O.energy_transfer(A[k], H)) < 1e-9
+    A = tensors(2, 8, 5, O)
+    M = np.stack([O.merge(A[k], A[k + 1]) for k in range(0, 8, 2)] + [O.merge(A[k + 1], A[k]) for k in range(0, 8, 2)])
+    e = B.energy_tensor(t.from_numpy(M).cuda(), H, two_site=True).cpu().numpy()
+    for k in range(4):
+        ref = O.energy_two_site_transfer(A[2 * k], A[2 * k + 1], H)
+        assert abs(0.5 * (e[k] + e[k + 4]) - ref) < 1e-9
+    U1, U2 = haar_batch(4, 2, 123)
+    assert abs(O.energy_two_site_statevector(U1, U2, H) - O.energy_two_site_transfer(O.unitary_to_tensor(U1), O.unitary_to_tensor(U2), H)) < 1e-12
+
+
+def test_rotosolve_fit_and_sweeps(env):
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    rng = np.random.default_rng(12)
+    c3 = rng.normal(size=(100, 3))
+    fit = B.rotosolve_fit(c3)
+    ref = np.array([O.rotosolve_theta3(*row) for row in c3])
+    assert np.abs(fit.theta_star.cpu().numpy() - ref).max() < 1e-13
+    c6 = rng.normal(size=(100, 6))
+    fit = B.rotosolve_fit(c6)
+    ref = np.array([O.double_rotosolve_fit(*row) for row in c6])
+    assert np.abs(fit.fit.cpu().numpy() - ref).max() < 1e-13
+    ts = fit.theta_star.cpu().numpy()
+    xs = np.linspace(-np.pi, np.pi, 20001)
+    for k in range(100):
+        a, b, c, d, P, u, Q, v = ref[k]
+        f = lambda x: P * np.sin(2 * x + u) + Q * np.sin(x + v)
+        assert f(ts[k]) <= f(xs).min() + 1e-9
+    # a device sweep never increases the energy and matches a host replay of the same rule
+    theta = rng.normal(size=(8, 12))
+    gate = R.ShallowCNOTStateTensor_nonuniform(4, theta[0])
+    H = O.tfim_matrix(1.0)
+    th = t.from_numpy(theta.copy()).cuda()
+    e0 = B.energy_theta(gate.program(), th, H).cpu().numpy()
+    e1 = B.rotosolve_sweeps(gate.program(), th, H, n_sweeps=1).cpu().numpy()
+    assert (e1 <= e0 + 1e-10).all()
+    host = theta[0].copy()
+    ef = lambda p: O.energy_transfer(O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(4, p)), H)
+    for i in range(12):
+        ei = np.eye(12)[i]
+        host[i] = O.rotosolve_step3(host[i], ef(host), ef(host + ei * np.pi / 2), ef(host - ei * np.pi / 2))
+    assert np.abs(th[0].cpu().numpy() - host).max() < 1e-8
+    assert abs(e1[0] - ef(host)) < 1e-9
+
+
+# ---------------------------------------------------------------- a11 Loschmidt pipeline
+def test_loschmidt_costs_d2_against_reference_circuit(env):
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    rng = np.random.default_rng(21)
+    theta = rng.normal(size=(6, 15))
+    A0 = O.unitary_to_tensor(O.shallow_full_state_tensor(rng.normal(size=15)))
+    W = np.stack([O.tfim_evolution_gate(0.2, 0.04 * k) for k in range(5)])
+    cost, echo, eta = B.loschmidt_costs(R.ShallowFullStateTensor(2, theta[0]).program(), theta, A0, W)
+    cost, echo = cost.cpu().numpy(), echo.cpu().numpy()
+    for p in range(6):
+        Bp = O.unitary_to_tensor(O.shallow_full_state_tensor(theta[p]))
+        for k in range(5):
+            assert abs(cost[p, k] - O.loschmidt_cost(A0, Bp, W[k])) < TOL * 10
+            assert abs(cost[p, k] - O.loschmidt_cost_circuit(A0, Bp, W[k])) < 1e-9      # the 6-qubit circuit
+            assert abs(echo[p, k] - 4 * (-np.log(-cost[p, k]))) < 1e-9
+
+
+def test_loschmidt_costs_d4(env):
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    rng = np.random.default_rng(2)
+    theta = rng.normal(size=(16, 12))
+    gate = R.ShallowCNOTStateTensor_nonuniform(4, theta[0])
+    A0 = O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(4, theta[0]))
+    W = np.stack([O.tfim_evolution_gate(0.2, 0.02 * k) for k in range(0, 1000, 97)])
+    cost, echo, _ = B.loschmidt_costs(gate.program(), theta, A0, W)
+    cost = cost.cpu().numpy()
+    assert abs(cost[0, 0] + 1) < 1e-12                      # k = 0, same state: overlap 1
+    for p in range(0, 16, 3):
+        Bp = O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(4, theta[p]))
+        for k in range(len(W)):
+            assert abs(cost[p, k] - O.loschmidt_cost(A0, Bp, W[k])) < TOL * 10
+
+
+def test_loschmidt_rate_vs_reference_golden(env, golden):
+    B = env["B"]
+    g = golden["ref_exact_loschmidt"]
+    got = B.loschmidt_rate(g["t"], 1.5, 0.2).cpu().numpy()
+    assert np.abs(got - g["g15_02"]).max() < 1e-8
+    got = B.loschmidt_rate(g["t"], 0.5, 2.0).cpu().numpy()
+    assert np.abs(got - g["g05_20"]).max() < 1e-6          # crosses DQPT cusps: log singularities
+
+
+# ---------------------------------------------------------------- cfg 5, (e)
+@pytest.mark.parametrize("D", [16, 64])
+def test_tm_power_vs_oracle(env, D):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A, Bt = tensors(D, 3, 400 + D, O), tensors(D, 3, 500 + D, O)
+    r, ray = B.tm_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), K=8)
+    for k in range(3):
+        r0, q0 = O.power_method(A[k], Bt[k], 8)
+        assert np.abs(r[k].cpu().numpy() - r0).max() < 1e-12
+        assert abs(ray[k].item() - q0) < 1e-12
+
+
+def test_argmin(env):
+    t, B = env["torch"], env["B"]
+    rng = np.random.default_rng(0)
+    for n in (1, 257, 100003):
+        c = rng.normal(size=n)
+        c[n // 3] = c.min() - 1
+        c[(2 * n) // 3] = c.min()                          # tie: the first index wins
+        bc, bi = B.argmin(t.from_numpy(c).cuda(), 1000)
+        assert bc.item() == c.min() and bi.item() == 1000 + int(np.argmin(c))
+
+
+# ---------------------------------------------------------------- drop-in numpy API
+def test_dropin_tools_against_reference_golden(env, golden):
+    from qmps_b200 import tools, time_evolve_tools as tet
+    O = env["O"]
+    g = golden["ref_tools"]
+    for D in (2, 4):
+        for U, Vref in zip(g[f"u2t_U_D{D}"], g[f"env_V_D{D}"]):
+            V = tools.get_env_exact(U)
+            assert np.abs(V[:, 0] - Vref[:, 0]).max() < 1e-10       # the unique column of the reference's V
+            assert np.abs(V.conj().T @ V - np.eye(D * D)).max() < 1e-12
+            assert np.array_equal(tools.unitary_to_tensor(U), O.unitary_to_tensor(U))
+    U, passed = tools.tensor_to_unitary(g["u2t_A_D2"][0], testing=True)
+    assert passed
+    ext = tools.unitary_extension(g["uext_tall_in"])
+    assert np.abs(ext[:, :3] - g["uext_tall_in"]).max() == 0 and np.abs(ext.conj().T @ ext - np.eye(6)).max() < 1e-13
+    ext = tools.unitary_extension(g["uext_wide_in"])
+    assert np.abs(ext[:3] - g["uext_wide_in"]).max() == 0 and np.abs(ext @ ext.conj().T - np.eye(6)).max() < 1e-13
+    assert tools.unitary_extension(g["uext_tall_in"], 8).shape == (8, 8)
+    assert np.array_equal(tools.environment_from_unitary(g["e2u_out"]), g["efu_out"])
+    # environments on a site: round trips (reference self-tests, new_time_evolve.py:53-70)
+    rng = np.random.default_rng(1)
+    q = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    for put, off in ((tet.put_env_on_left_site, tet.get_env_off_left_site), (tet.put_env_on_right_site, tet.get_env_off_right_site)):
+        Aq, n = put(q, ret_n=True)
+        assert np.abs(Aq.conj().T @ Aq - np.eye(4)).max() < 1e-13
+        assert np.abs(off(Aq) * n - q).max() < 1e-13
+    p1, p2 = rng.normal(size=15), rng.normal(size=15)
+    f, r = tet.get_overlap_exact(p1, p2)
+    f0, r0 = O.get_overlap_exact(p1, p2)
+    assert abs(f - f0) < 1e-10
+    assert abs(tet.get_overlap_exact(p1, p1, testing=False) - 1) < 1e-12
+    A, Bt = tensors(2, 2, 77, O)
+    assert np.abs(tet.merge(A, Bt) - O.merge(A, Bt)).max() < 1e-14
+
+
+def test_dropin_ground_state(env):
+    from qmps_b200 import ground_state as gs
+    O = env["O"]
+    H = gs.Hamiltonian({"ZZ": -1, "X": 1}).to_matrix()
+    assert np.array_equal(H, O.tfim_matrix(1.0))
+    opt = gs.SparseFullEnergyOptimizer(H, D=2, depth=2, initial_guess=np.array([0.3, -0.2, 0.5, 0.1]))
+    e = opt.objective_function(opt.initial_guess)
+    assert abs(e - O.energy_transfer(O.unitary_to_tensor(O.shallow_cnot_state_tensor(2, opt.initial_guess)), H)) < 1e-10
+    rng = np.random.default_rng(3)
+    p = rng.normal(size=15)
+    opt = gs.NonSparseFullEnergyOptimizer(H, D=2, initial_guess=p)
+    assert abs(opt.objective_function(p) - O.energy_transfer(O.unitary_to_tensor(gs.SU(p, 4)), H)) < 1e-10
+    p = rng.normal(size=30)
+    opt2 = gs.NonSparseFullTwoSiteEnergyOptimizer(H, initial_guess=p)
+    ref = O.energy_two_site_statevector(gs.SU(p[:15], 4), gs.SU(p[15:], 4), H)
+    assert abs(opt2.objective_function(p) - ref) < 1e-10
+
+
+def test_env_exact_host_entry_point(env):
+    """The host-buffer C ABI call (what bench.py's e2e leg times)."""
+    import ctypes
+    L, O = env["L"], env["O"]
+    N = 5000
+    A = np.tile(tensors(2, 50, 600, O), (100, 1, 1, 1))
+    eta = np.empty(N, np.complex128); r = np.empty((N, 2, 2), np.complex128)
+    C = np.empty((N, 2, 2), np.complex128); st = np.empty(N, np.int32)
+    rc = L.load().qmps_env_exact_host(2, 2, N, A.ctypes.data, 0, 1, eta.ctypes.data, r.ctypes.data, C.ctypes.data,
+                                      st.ctypes.data, L.C128, 0)
+    L.check(rc, "env_exact_host")
+    assert st.sum() == 0
+    for k in range(50):
+        _, r0, C0, _ = O.env_exact_parts(A[k])
+        assert np.abs(r[k] - r0).max() < 1e-10 and np.abs(r[k + 50 * 99] - r0).max() < 1e-10
+        assert np.abs(C[k] - C0).max() < 1e-9
