@@ -347,7 +347,9 @@ def test_rotosolve_fit_and_sweeps(env):
     for i in range(12):
         ei = np.eye(12)[i]
         host[i] = O.rotosolve_step3(host[i], ef(host), ef(host + ei * np.pi / 2), ef(host - ei * np.pi / 2))
-    assert np.abs(th[0].cpu().numpy() - host).max() < 1e-8
+    # coordinate 0 is rz on the |0> input qubit: a global phase, the cost is flat in it and the
+    # closed-form angle is atan2(noise, noise); every other coordinate must agree
+    assert np.abs(th[0].cpu().numpy() - host)[1:].max() < 1e-8
     assert abs(e1[0] - ef(host)) < 1e-9
 
 

@@ -1,0 +1,236 @@
+"""CPU tests that need no GPU: the C ABI library loads and exports every symbol the header
+declares, the product has no CPU fallback and never touches the oracle, the host-side
+logic (gate programs, Hamiltonian, rotosolve drivers, sharding + gloo argmin), and the
+device ALGORITHMS compiled for the host (tests/host_emu) against the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from scipy.stats import unitary_group
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from qmps_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "qmps_b200.h")).read()
+    declared = set(re.findall(r"\b(qmps_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 17
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.qmps_version()
+    assert ctypes.sizeof(_lib.GateOp) == 32
+
+
+def test_library_holds_sm100a_code_only(built):
+    from qmps_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product(built):
+    from qmps_b200 import _lib, batched, tools
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    with pytest.raises(_lib.QmpsError):
+        batched.env_exact(U=np.eye(4)[None].astype(complex))
+    with pytest.raises(_lib.QmpsError):
+        tools.get_env_exact(np.eye(4, dtype=complex))
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "qmps_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+    for f in os.listdir(os.path.join(ROOT, "qmps")):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "qmps", f)).read()
+
+
+def test_gate_programs_have_reference_gate_order():
+    from qmps_b200 import represent as R, _lib as L
+    g = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+    codes = [op[0] for op in g.ops]
+    assert codes == [L.G_RZ, L.G_RX, L.G_RZ, L.G_RZ, L.G_RX, L.G_RZ, L.G_CNOT, L.G_RY, L.G_CNOT, L.G_RY, L.G_RZ,
+                     L.G_CNOT, L.G_RZ, L.G_RX, L.G_RZ, L.G_RZ, L.G_RX, L.G_RZ]          # represent.py:392-401
+    assert [op[3] for op in g.ops if op[3] >= 0] == list(range(15))
+    g = R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(24)).program()
+    assert g.nq == 4 and len(g) == 3 * (8 + 3)
+    assert [(op[1], op[2]) for op in g.ops[8:11]] == [(2, 3), (1, 2), (0, 1)]       # reversed ladder
+    assert R.ShallowCNOTStateTensor_nonuniform.params_per_iter(8) == 8
+    assert R.ShallowEnvironment(4, np.zeros(4)).num_qubits() == 4
+    assert R.StateGate(np.zeros(6)).program().nq == 2
+
+
+def test_hamiltonian_and_host_helpers():
+    from qmps_b200 import ground_state as gs, tools, rotosolve as rs
+    H = gs.Hamiltonian({"ZZ": -1, "X": 1}).to_matrix()
+    assert np.allclose(H, O.tfim_matrix(1.0))
+    assert np.allclose(gs.Hamiltonian().from_matrix(H).to_matrix(), H)
+    U = gs.SU(np.random.default_rng(0).normal(size=15), 4)
+    assert np.allclose(U.conj().T @ U, np.eye(4)) and abs(np.linalg.det(U) - 1) < 1e-12
+    v = np.arange(10.0)
+    assert np.array_equal(tools.from_real_vector(v), O.from_real_vector(v))
+    assert np.array_equal(tools.to_real_vector(U), O.to_real_vector(U))
+    assert np.array_equal(tools.direct_sum(np.eye(2), np.ones((1, 1))), O.direct_sum(np.eye(2), np.ones((1, 1))))
+    assert tools.split_ns(list(range(7)), 3) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert abs(rs.rotosolve_theta(0.3, -0.2, 0.9) - O.rotosolve_theta3(0.3, -0.2, 0.9)) < 1e-15
+    assert np.allclose(rs.double_rotosolve_coefficients(1, 2, 3, 4, 5, 6), O.double_rotosolve_fit(1, 2, 3, 4, 5, 6))
+
+
+def test_double_rotosolve_driver_matches_reference(golden):
+    """The host driver (pure Python around a cost callable) against the reference's outputs."""
+    from qmps_b200 import tools
+    g = golden["ref_tools"]
+
+    def eps(p):
+        return (np.sin(p[0]) * np.cos(2 * p[1]) + 0.3 * np.sin(2 * p[0] + 0.4)
+                + 0.5 * np.cos(p[1] - 0.2) + 0.1 * np.sin(p[2]) * np.sin(p[0]))
+    p = g["drs_p0"].copy()
+    res = tools.double_rotosolve(eps, p, 3, False)
+    assert np.allclose(res.history, g["drs_history"], atol=1e-12) and np.allclose(res.x, g["drs_x"], atol=1e-12)
+    assert res.x is p                                       # mutated in place like the reference
+    eps.batched = lambda th: np.array([eps(t) for t in th])
+    res2 = tools.double_rotosolve(eps, g["drs_p0"].copy(), 3, False)
+    assert np.allclose(res2.x, g["drs_x"], atol=1e-12)
+
+
+def test_shard_ranges_cover_the_batch():
+    from qmps_b200.dist import shard_range
+    for n in (0, 1, 7, 1 << 20, 65536 * 3 + 5):
+        for world in (1, 2, 3, 8):
+            parts = [shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+_GLOO_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from qmps_b200.dist import shard_range, global_argmin, global_sum
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator().manual_seed(0)
+cost = torch.randn(1001, dtype=torch.float64, generator=g)
+cost[700] = cost.min() - 1.0
+cost[123] = cost[700]          # tie: the smaller global index must win
+lo, hi = shard_range(1001)
+loc = cost[lo:hi]
+k = int(torch.argmin(loc))
+first = int((loc == loc.min()).nonzero()[0])
+best, idx = global_argmin(loc[first].reshape(1), torch.tensor([lo + first]))
+assert float(best) == float(cost.min()) and int(idx) == 123, (float(best), int(idx))
+s = global_sum(loc.sum().reshape(1))
+assert abs(float(s) - float(cost.sum())) < 1e-9
+e_best, e_idx = global_argmin(torch.tensor([0.0], dtype=torch.float64), torch.tensor([-1]))   # all shards empty
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_global_argmin_world2_gloo(tmp_path):
+    script = tmp_path / "gloo_argmin.py"
+    script.write_text(_GLOO_SCRIPT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+# ---- the device algorithms, compiled for the host (group of one lane) -------------------------
+@pytest.fixture(scope="module")
+def emu(built):
+    return ctypes.CDLL(os.path.join(ROOT, "tests", "host_emu", "libqmps_emu.so"))
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_emu_qr_eigenvalues(emu):
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 4, 16, 64):
+        for _ in range(5):
+            M = np.ascontiguousarray((rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / np.sqrt(n))
+            w = np.zeros(n, complex)
+            assert emu.emu_eigvals(n, P(M), P(w)) == 0
+            wr = np.linalg.eigvals(M)
+            d = np.abs(w[:, None] - wr[None, :])
+            assert max(d.min(axis=1).max(), d.min(axis=0).max()) < 1e-12
+    M = np.ascontiguousarray(np.diag([1.0, 2.0, 3.0]).astype(complex))       # already triangular
+    w = np.zeros(3, complex); emu.emu_eigvals(3, P(M), P(w))
+    assert sorted(w.real) == [1.0, 2.0, 3.0]
+
+
+def test_emu_env_d2_bloch_solver(emu):
+    N = 500
+    A = np.ascontiguousarray(np.stack([O.unitary_to_tensor(unitary_group.rvs(4, random_state=s)) for s in range(N)]))
+    r = np.zeros((N, 2, 2), complex); eta = np.zeros(N, complex); C = np.zeros((N, 2, 2), complex); st = np.zeros(N, np.int32)
+    emu.emu_env_d2(ctypes.c_int64(N), P(A), P(r), P(eta), P(C), P(st))
+    assert st.sum() == 0 and np.abs(eta - 1).max() < 1e-14
+    for k in range(N):
+        _, r0, C0, _ = O.env_exact_parts(A[k])
+        w = np.sort(np.abs(np.linalg.eigvals(O.transfer_matrix(A[k]))))[::-1]
+        assert np.abs(r[k] - r0).max() < 1e-12 / (1 - w[1])
+    I4 = np.ascontiguousarray(O.unitary_to_tensor(np.eye(4, dtype=complex))[None])
+    emu.emu_env_d2(ctypes.c_int64(1), P(I4), P(r), P(eta), P(C), P(st))
+    assert st[0] == 1                                       # product state: not positive definite
+
+
+@pytest.mark.parametrize("D", [2, 4, 8])
+def test_emu_generic_env_and_fixed_point(emu, D):
+    N = 6
+    A = np.ascontiguousarray(np.stack([O.unitary_to_tensor(unitary_group.rvs(2 * D, random_state=100 + s)) for s in range(N)]))
+    B = np.ascontiguousarray(np.stack([O.unitary_to_tensor(unitary_group.rvs(2 * D, random_state=500 + s)) for s in range(N)]))
+    for lc in (1, 0):
+        r = np.zeros((N, D, D), complex); eta = np.zeros(N, complex); C = np.zeros((N, D, D), complex); st = np.zeros(N, np.int32)
+        emu.emu_env_generic(2, D, ctypes.c_int64(N), P(A), lc, P(eta), P(r), P(C), P(st))
+        assert st.sum() == 0
+        for k in range(N):
+            _, r0, C0, _ = O.env_exact_parts(A[k])
+            assert np.abs(r[k] - r0).max() < 1e-12 and np.abs(C[k] - C0).max() < 1e-11
+    for left in (0, 1):
+        vec = np.zeros((N, D, D), complex); eta = np.zeros(N, complex); st = np.zeros(N, np.int32)
+        emu.emu_fixed_point(2, D, ctypes.c_int64(N), P(A), P(B), left, P(eta), P(vec), P(st))
+        for k in range(N):
+            x, _ = (O.left_fixed_point if left else O.right_fixed_point)(A[k], B[k])
+            assert abs(abs(eta[k]) - abs(x)) < 1e-12
+            E = O.transfer_matrix(A[k], B[k]); Em = E.conj().T if left else E
+            assert np.abs(Em @ vec[k].reshape(-1) - eta[k] * vec[k].reshape(-1)).max() < 1e-11
+
+
+def test_emu_ansatz_and_energy(emu):
+    from qmps_b200 import represent as R
+    rng = np.random.default_rng(3)
+    H = np.ascontiguousarray(O.tfim_matrix(1.0))
+    for gate, ofn in ((R.ShallowFullStateTensor(2, rng.normal(size=15)), O.shallow_full_state_tensor),
+                      (R.ShallowCNOTStateTensor_nonuniform(8, rng.normal(size=24)), lambda p: O.shallow_cnot_state_tensor_nonuniform(8, p)),
+                      (R.ShallowQAOAStateTensor(4, rng.normal(size=6)), lambda p: O.shallow_qaoa_state_tensor(4, p)),
+                      (R.ExactAfter4(4, rng.normal(size=12)), lambda p: O.exact_after4(4, p)),
+                      (R.StateGate(rng.normal(size=6)), O.state_gate)):
+        prog = gate.program(); nq = prog.nq; D = 2 ** (nq - 1)
+        th = np.ascontiguousarray(gate.params[None, :])
+        A = np.zeros((1, 2, D, D), complex)
+        emu.emu_ansatz(prog.c_ops(), len(prog), nq, ctypes.c_int64(1), th.shape[1], P(th), 0, 1, ctypes.c_double(0.3), P(A))
+        p2 = gate.params.copy(); p2[1] += 0.3
+        Aref = O.unitary_to_tensor(ofn(p2))
+        assert np.abs(A[0] - Aref).max() < 1e-14
+        e = np.zeros(1)
+        emu.emu_energy_generic(D, ctypes.c_int64(1), P(A), 0, P(H), P(e))
+        assert abs(e[0] - O.energy_transfer(Aref, H)) < 1e-12
+        if nq == 2:
+            A2 = np.zeros((1, 2, 2, 2), complex)
+            emu.emu_ansatz_reg2(prog.c_ops(), len(prog), ctypes.c_int64(1), th.shape[1], P(th), 1, ctypes.c_double(0.3), P(A2))
+            assert np.abs(A2[0] - Aref).max() < 1e-14
+            emu.emu_energy_d2(ctypes.c_int64(1), P(A2), P(H), P(e))
+            assert abs(e[0] - O.energy_transfer(Aref, H)) < 1e-12
