@@ -150,12 +150,17 @@ def run_reference(args):
 # GPU side
 # ------------------------------------------------------------------------------------------
 def make_tensors(torch, n, seed, device):
-    """n random left-canonical tensors A[n,2,2,2] (first two columns of Haar unitaries via QR)."""
+    """n random left-canonical tensors A[n,2,2,2]: the first two columns of Haar unitaries, by
+    two-column Gram-Schmidt in a handful of elementwise launches (set-up only, not timed; kept
+    cheap so that the ncu launch list of this command is dominated by the timed kernel)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    Z = torch.randn((n, 4, 2), dtype=torch.float64, device=device, generator=g) \
-        + 1j * torch.randn((n, 4, 2), dtype=torch.float64, device=device, generator=g)
-    Q, _ = torch.linalg.qr(Z)
-    return Q.reshape(n, 2, 2, 2).permute(0, 2, 1, 3).contiguous()
+    Z = torch.randn((n, 4, 2, 2), dtype=torch.float64, device=device, generator=g)
+    Z = torch.view_as_complex(Z)                                   # [n, 4, 2]
+    q1 = Z[:, :, 0] / Z[:, :, 0].norm(dim=1, keepdim=True)
+    z2 = Z[:, :, 1] - q1 * (q1.conj() * Z[:, :, 1]).sum(dim=1, keepdim=True)
+    q2 = z2 / z2.norm(dim=1, keepdim=True)
+    Q = torch.stack([q1, q2], dim=2)                               # iso[(i,s), j]
+    return Q.reshape(n, 2, 2, 2).permute(0, 2, 1, 3).contiguous()  # A[s, i, j]
 
 
 def run_ours(args):

@@ -6,6 +6,7 @@
 
 #include "api_common.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_gemm.cuh"
 
 using namespace qmps;
 using namespace qmps_host;
@@ -59,6 +60,46 @@ int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r
   CK(cudaGetLastError());
   CK(cudaFreeAsync(Tb, st));
   CK(cudaFreeAsync(invn, st));
+  return 0;
+}
+
+
+// complex128: DMMA tiles (kernels_gemm.cuh); two launches per application, norms carried as
+// per-tile partial sums so that no separate normalisation pass touches r.
+int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh,
+                 cudaStream_t st) {
+  if (N == 0) return 0;
+  typedef cx<double> Z;
+  const size_t DD = (size_t)D * D;
+  const int tx = (D + ZG_TN - 1) / ZG_TN, ty = (D + ZG_TM - 1) / ZG_TM, tiles = tx * ty;
+  Z* Tb = nullptr; Z* Er = nullptr; double* nrm = nullptr;
+  CK(cudaMallocAsync((void**)&Tb, sizeof(Z) * N * d * DD, st));
+  CK(cudaMallocAsync((void**)&nrm, sizeof(double) * N * tiles, st));
+  if (int rc = allow_smem(zgemm_dmma_kernel<0>, ZG_SMEM_BYTES)) return rc;
+  if (int rc = allow_smem(zgemm_dmma_kernel<1>, ZG_SMEM_BYTES)) return rc;
+  Z* r = (Z*)r_io;
+  const dim3 grid1(tx, ty, (unsigned)(N * d)), grid2(tx, ty, (unsigned)N);
+  auto apply = [&](Z* dst, const double* norm_in, double* norm_out) {
+    ZgParams p1;
+    p1.M = D; p1.N = D; p1.K = D; p1.nsum = 1; p1.A = (const Z*)A; p1.B = r; p1.b_div = d; p1.C = Tb;
+    p1.norm_in = norm_in; p1.n_in = tiles; p1.norm_out = nullptr;
+    zgemm_dmma_kernel<0><<<grid1, 256, ZG_SMEM_BYTES, st>>>(p1);
+    ZgParams p2;
+    p2.M = D; p2.N = D; p2.K = D; p2.nsum = d; p2.A = Tb; p2.B = (const Z*)B; p2.b_div = 1; p2.C = dst;
+    p2.norm_in = nullptr; p2.n_in = 0; p2.norm_out = norm_out;
+    zgemm_dmma_kernel<1><<<grid2, 256, ZG_SMEM_BYTES, st>>>(p2);
+  };
+  for (int it = 0; it < K; ++it) apply(r, it == 0 ? nullptr : nrm, nrm);
+  if (K > 0) zg_scale_kernel<<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, nrm, tiles);
+  if (rayleigh) {
+    CK(cudaMallocAsync((void**)&Er, sizeof(Z) * N * DD, st));
+    apply(Er, nullptr, nullptr);
+    vdot_kernel<double><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (Z*)rayleigh);
+    CK(cudaFreeAsync(Er, st));
+  }
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(Tb, st));
+  CK(cudaFreeAsync(nrm, st));
   return 0;
 }
 
@@ -255,7 +296,7 @@ int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r
                   int dtype, void* stream) {
   if (d < 1 || D < 1 || N < 0 || K < 0 || (N && (!A || !B || !r_io))) return fail(QMPS_ERR_ARG, "tm_power: bad arguments");
   if (N * d > 65535) return fail(QMPS_ERR_UNSUPPORTED, "tm_power: N*d > 65535 (split the batch)");
-  if (dtype == QMPS_C128) return tm_power_impl<double>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
+  if (dtype == QMPS_C128) return tm_power_f64(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
   if (dtype == QMPS_C64) return tm_power_impl<float>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
   return fail(QMPS_ERR_ARG, "tm_power: bad dtype");
 }

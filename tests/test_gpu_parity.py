@@ -396,15 +396,39 @@ def test_loschmidt_rate_vs_reference_golden(env, golden):
 
 
 # ---------------------------------------------------------------- cfg 5, (e)
-@pytest.mark.parametrize("D", [16, 64])
+@pytest.mark.parametrize("D", [16, 64, 100, 256])
 def test_tm_power_vs_oracle(env, D):
+    """cfg 5: D = 100 exercises the ragged edges of the 64 x 64 DMMA tiles, 256 the multi-tile norm."""
     t, B, O = env["torch"], env["B"], env["O"]
-    A, Bt = tensors(D, 3, 400 + D, O), tensors(D, 3, 500 + D, O)
+    cnt = 3 if D <= 100 else 2
+    A, Bt = tensors(D, cnt, 400 + D, O), tensors(D, cnt, 500 + D, O)
     r, ray = B.tm_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), K=8)
-    for k in range(3):
+    for k in range(cnt):
         r0, q0 = O.power_method(A[k], Bt[k], 8)
         assert np.abs(r[k].cpu().numpy() - r0).max() < 1e-12
         assert abs(ray[k].item() - q0) < 1e-12
+
+
+def test_tm_power_same_tensor_converges_to_environment(env):
+    """Size-independent property: for A = B left-canonical the power method converges to the
+    exact environment of the direct solver (trace-normalised), Rayleigh quotient -> 1."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = t.from_numpy(tensors(16, 4, 77, O)).cuda()
+    r, ray = B.tm_power(A, A, K=400)
+    ex = B.env_exact(A=A, want_C=False)
+    rn = r / t.einsum("nii->n", r)[:, None, None]
+    assert (rn - ex.r).abs().max().item() < 1e-9
+    assert (ray - 1).abs().max().item() < 1e-9
+
+
+def test_tm_power_complex64(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A, Bt = tensors(64, 2, 464, O), tensors(64, 2, 564, O)
+    r, ray = B.tm_power(t.from_numpy(A).cuda().to(t.complex64), t.from_numpy(Bt).cuda().to(t.complex64), K=8)
+    for k in range(2):
+        r0, q0 = O.power_method(A[k], Bt[k], 8)
+        assert np.abs(r[k].cpu().numpy() - r0).max() < 1e-5
+        assert abs(ray[k].item() - q0) < 1e-5
 
 
 def test_argmin(env):

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Launches each hot kernel a few times on cheap synthetic inputs -- the target of the
+`ncu --set full -k regex:...` captures (tools/gpu_round.sh).  Inputs come from this repo's own
+ansatz kernel (theta -> left-canonical A), so almost every launch ncu sees is one of ours.
+
+  python tools/profile_driver.py [--what d2,fp4,en8,pw64,pw256] [--reps 3]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="d2,fp4,en8,pw64")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    from qmps_b200 import batched as B, represent as R
+    from qmps_b200.ground_state import Hamiltonian
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    what = args.what.split(",")
+    g = torch.Generator(device=dev).manual_seed(0)
+
+    def thetas(n, p):
+        return torch.randn((n, p), dtype=torch.float64, device=dev, generator=g)
+
+    def lc_tensors(n, D, layers=3):
+        nq = int(np.log2(D)) + 1
+        prog = R.ShallowCNOTStateTensor_nonuniform(D, np.zeros(2 * nq * layers)).program()
+        return B.ansatz_tensors(prog, thetas(n, 2 * nq * layers))
+
+    if "d2" in what:
+        N = 1 << 20
+        As = [lc_tensors(N, 2) for _ in range(2)]
+        for i in range(args.reps + 2):
+            B.env_exact(A=As[i & 1], want_C=False, want_status=False)
+    if "fp4" in what:                      # cfg 3 tile: 16x16 mixed two-site maps
+        NP, NT = 512, 64
+        prog = R.ShallowCNOTStateTensor_nonuniform(4, np.zeros(12)).program()
+        th = thetas(NP, 12)
+        A0 = B.ansatz_tensors(prog, th[:1])[0]
+        from scipy.linalg import expm
+        H = Hamiltonian({'ZZ': -1, 'X': 0.2}).to_matrix()
+        W = torch.from_numpy(np.stack([expm(-1j * H * 0.04 * k) for k in range(NT)])).to(dev)
+        for _ in range(args.reps):
+            B.loschmidt_costs(prog, th, A0, W)
+    if "en8" in what:                      # cfg 4 tile: D=8 energy with 3 shifts
+        prog = R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(24)).program()
+        th = thetas(8192, 24)
+        H = Hamiltonian({'XX': 1, 'YY': 1, 'ZZ': 1}).to_matrix()
+        for _ in range(args.reps):
+            B.energy_theta(prog, th, H, coord=5, shifts=B.ROTO3_SHIFTS)
+    for tag, D, N in (("pw64", 64, 512), ("pw256", 256, 32)):
+        if tag in what:
+            A = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float64, device=dev, generator=g)) / np.sqrt(2 * D)
+            Bt = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float64, device=dev, generator=g)) / np.sqrt(2 * D)
+            for _ in range(args.reps):
+                B.tm_power(A, Bt, 2)
+    torch.cuda.synchronize()
+    print("profile_driver done:", what)
+
+
+if __name__ == "__main__":
+    main()
