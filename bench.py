@@ -197,15 +197,16 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # long enough for nvidia-smi to see the kernel: repeat the K-step block if it is very short
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # two events around the K back-to-back launches (an event between launches would serialise them)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev[0].record()
+    ev0.record()
     for i in range(args.steps):
         step(i)
-        ev[i + 1].record()
+    ev1.record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev0.elapsed_time(ev1)
+    per_launch_ms = [total_ms / args.steps]
     # keep the GPU busy a little longer so that the clock sampler has samples under load
     if rank == 0:
         t_end = time.time() + 0.6

@@ -250,10 +250,12 @@ def power_method(A, B, K, r0=None):
     (r_K, rayleigh) with rayleigh = <r_K, E r_K> for the unit-norm r_K."""
     D = A.shape[1]
     r = np.eye(D, dtype=np.complex128) / np.sqrt(D) if r0 is None else r0.astype(np.complex128)
+    Bh = np.conj(np.swapaxes(B, -1, -2))
+    apply = lambda x: np.sum(A @ x @ Bh, axis=0)      # sum_s A_s x B_s^dagger
     for _ in range(K):
-        r = np.einsum("sij,jl,skl->ik", A, r, B.conj())
+        r = apply(r)
         r = r / np.linalg.norm(r)
-    Er = np.einsum("sij,jl,skl->ik", A, r, B.conj())
+    Er = apply(r)
     return r, np.vdot(r, Er)
 
 

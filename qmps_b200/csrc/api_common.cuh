@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <string.h>
 #include <string>
+#include <mutex>
+#include <unordered_map>
+#include <functional>
 
 #include "../../include/qmps_b200.h"
 #include "kernels_generic.cuh"
@@ -19,21 +22,50 @@ inline int fail(int code, const std::string& msg) { last_error() = msg; return c
       return qmps_host::fail(QMPS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// tuning knobs (qmps_set_option); defaults are the measured best
+enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_COUNT = 8 };
+int option_get(int key);                          // defined in capi.cu
+
 inline int sm_count() {
+  static int cached[64] = {0};
   int dev = 0, v = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  if (dev >= 0 && dev < 64) cached[dev] = v;
   return v;
 }
 
 inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// per-(kernel, block, smem) launch set-up is cached: the occupancy query and the shared-memory
+// opt-in cost microseconds of host time, which matters for 40 us kernels launched back to back
+struct LaunchKey {
+  const void* fn; int block; size_t smem;
+  bool operator==(const LaunchKey& o) const { return fn == o.fn && block == o.block && smem == o.smem; }
+};
+struct LaunchKeyHash {
+  size_t operator()(const LaunchKey& k) const { return std::hash<const void*>()(k.fn) ^ (k.smem * 1315423911u) ^ (size_t)k.block; }
+};
+std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache();   // defined in capi.cu
+std::mutex& occupancy_mutex();
+
 // persistent grid: one wave of resident CTAs (SM count x occupancy), never more than needed
 template <typename K>
 int persistent_grid(K kernel, int block, size_t smem, int64_t blocks_needed, int* out_grid) {
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
-  if (e != cudaSuccess) return fail(QMPS_ERR_CUDA, std::string("occupancy: ") + cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lock(occupancy_mutex());
+    auto& cache = occupancy_cache();
+    LaunchKey key{(const void*)kernel, block, smem};
+    auto it = cache.find(key);
+    if (it != cache.end()) per_sm = it->second;
+    else {
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+      if (e != cudaSuccess) return fail(QMPS_ERR_CUDA, std::string("occupancy: ") + cudaGetErrorString(e));
+      cache[key] = per_sm;
+    }
+  }
   if (per_sm < 1) return fail(QMPS_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
   int64_t cap = (int64_t)sm_count() * per_sm;
   int64_t g = blocks_needed < cap ? blocks_needed : cap;
@@ -42,15 +74,45 @@ int persistent_grid(K kernel, int block, size_t smem, int64_t blocks_needed, int
 }
 
 template <typename K> int allow_smem(K kernel, size_t smem) {
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem <= 48 * 1024) return 0;
+  {
+    std::lock_guard<std::mutex> lock(occupancy_mutex());
+    auto& cache = occupancy_cache();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    LaunchKey key{(const void*)kernel, -1 - dev, smem};       // block < 0: "opt-in done on device -1-block"
+    if (cache.find(key) != cache.end()) return 0;
+    cache[key] = 1;
+  }
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return 0;
+}
+
+// The stream-ordered allocator returns freed memory to the driver at the next synchronisation
+// unless a release threshold is set; scratch buffers of tens of MiB would then be re-mapped on
+// every call (milliseconds).  Keep the pool: once per device.
+inline void keep_mempool() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
+inline cudaError_t malloc_async(void** ptr, size_t bytes, cudaStream_t st) {
+  keep_mempool();
+  return cudaMallocAsync(ptr, bytes, st);
 }
 
 // stream-ordered device copy of a small host array
 template <typename U> int to_device_async(const U* host, size_t count, U** dev, cudaStream_t st) {
   *dev = nullptr;
   if (count == 0) return 0;
-  CK(cudaMallocAsync((void**)dev, count * sizeof(U), st));
+  CK(malloc_async((void**)dev, count * sizeof(U), st));
   CK(cudaMemcpyAsync(*dev, host, count * sizeof(U), cudaMemcpyHostToDevice, st));
   return 0;
 }

@@ -16,6 +16,10 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 0 /* d2_ctas_per_sm: 0 = occupancy */, 0, 0, 0, 0, 0, 0};
+std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
+std::mutex& occupancy_mutex() { static std::mutex m; return m; }
+int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 }
 
 namespace {
@@ -37,8 +41,8 @@ int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r
   if (N == 0) return 0;
   const size_t DD = (size_t)D * D;
   cx<T>* Tb = nullptr; cx<T>* Er = nullptr; T* invn = nullptr;
-  CK(cudaMallocAsync((void**)&Tb, sizeof(cx<T>) * N * d * DD, st));
-  CK(cudaMallocAsync((void**)&invn, sizeof(T) * N, st));
+  CK(malloc_async((void**)&Tb, sizeof(cx<T>) * N * d * DD, st));
+  CK(malloc_async((void**)&invn, sizeof(T) * N, st));
   cx<T>* r = (cx<T>*)r_io;
   const dim3 grid1((D + 31) / 32, (D + 31) / 32, (unsigned)(N * d)), grid2((D + 31) / 32, (D + 31) / 32, (unsigned)N);
   auto apply = [&](cx<T>* dst) {
@@ -52,7 +56,7 @@ int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r
     scale_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, invn);
   }
   if (rayleigh) {
-    CK(cudaMallocAsync((void**)&Er, sizeof(cx<T>) * N * DD, st));
+    CK(malloc_async((void**)&Er, sizeof(cx<T>) * N * DD, st));
     apply(Er);
     vdot_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (cx<T>*)rayleigh);
     CK(cudaFreeAsync(Er, st));
@@ -73,8 +77,8 @@ int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_
   const size_t DD = (size_t)D * D;
   const int tx = (D + ZG_TN - 1) / ZG_TN, ty = (D + ZG_TM - 1) / ZG_TM, tiles = tx * ty;
   Z* Tb = nullptr; Z* Er = nullptr; double* nrm = nullptr;
-  CK(cudaMallocAsync((void**)&Tb, sizeof(Z) * N * d * DD, st));
-  CK(cudaMallocAsync((void**)&nrm, sizeof(double) * N * tiles, st));
+  CK(malloc_async((void**)&Tb, sizeof(Z) * N * d * DD, st));
+  CK(malloc_async((void**)&nrm, sizeof(double) * N * tiles, st));
   if (int rc = allow_smem(zgemm_dmma_kernel<0>, ZG_SMEM_BYTES)) return rc;
   if (int rc = allow_smem(zgemm_dmma_kernel<1>, ZG_SMEM_BYTES)) return rc;
   Z* r = (Z*)r_io;
@@ -92,7 +96,7 @@ int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_
   for (int it = 0; it < K; ++it) apply(r, it == 0 ? nullptr : nrm, nrm);
   if (K > 0) zg_scale_kernel<<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, nrm, tiles);
   if (rayleigh) {
-    CK(cudaMallocAsync((void**)&Er, sizeof(Z) * N * DD, st));
+    CK(malloc_async((void**)&Er, sizeof(Z) * N * DD, st));
     apply(Er, nullptr, nullptr);
     vdot_kernel<double><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (Z*)rayleigh);
     CK(cudaFreeAsync(Er, st));
@@ -110,6 +114,12 @@ extern "C" {
 
 const char* qmps_version(void) { return "qmps_b200 0.1.0 (sm_100a)"; }
 const char* qmps_last_error(void) { return last_error().c_str(); }
+int qmps_set_option(const char* name, int value) {
+  if (!name) return fail(QMPS_ERR_ARG, "set_option: null name");
+  if (!strcmp(name, "d2_pdl")) { g_options[OPT_D2_PDL] = value; return 0; }
+  if (!strcmp(name, "d2_ctas_per_sm")) { g_options[OPT_D2_CTAS_PER_SM] = value; return 0; }
+  return fail(QMPS_ERR_ARG, std::string("set_option: unknown option ") + name);
+}
 int qmps_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -309,9 +319,9 @@ int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* bes
   if (grid > sm_count() * 4) grid = sm_count() * 4;
   if (grid < 1) grid = 1;
   double* bc = nullptr; int64_t* bi = nullptr; unsigned int* ctr = nullptr;
-  CK(cudaMallocAsync((void**)&bc, sizeof(double) * grid, st));
-  CK(cudaMallocAsync((void**)&bi, sizeof(int64_t) * grid, st));
-  CK(cudaMallocAsync((void**)&ctr, sizeof(unsigned int), st));
+  CK(malloc_async((void**)&bc, sizeof(double) * grid, st));
+  CK(malloc_async((void**)&bi, sizeof(int64_t) * grid, st));
+  CK(malloc_async((void**)&ctr, sizeof(unsigned int), st));
   CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
   argmin_kernel<<<grid, 256, 0, st>>>(N, cost, index_offset, bc, bi, ctr, best_cost, best_index);
   CK(cudaGetLastError());

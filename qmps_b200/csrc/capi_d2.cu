@@ -16,8 +16,20 @@ int env_exact_d2_c128(int64_t N, const void* in, int in_is_U, void* eta, void* r
     auto kern = env_d2_stream_kernel<INU, WC>;                                                            \
     if (int rc = allow_smem(kern, D2_SMEM_BYTES)) return rc;                                              \
     if (int rc = persistent_grid(kern, D2_WARPS * 32, D2_SMEM_BYTES, blocks, &grid)) return rc;          \
-    kern<<<grid, D2_WARPS * 32, D2_SMEM_BYTES, st>>>((const cx<double>*)in, N, (cx<double>*)eta,          \
-                                                     (cx<double>*)r, (cx<double>*)C, status);             \
+    if (option_get(OPT_D2_CTAS_PER_SM) > 0) {                                                             \
+      const int64_t cap = (int64_t)sm_count() * option_get(OPT_D2_CTAS_PER_SM);                           \
+      if (grid > cap) grid = (int)cap;                                                                    \
+    }                                                                                                     \
+    cudaLaunchConfig_t cfg;                                                                               \
+    memset(&cfg, 0, sizeof(cfg));                                                                         \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(D2_WARPS * 32);                                         \
+    cfg.dynamicSmemBytes = D2_SMEM_BYTES; cfg.stream = st;                                                \
+    cudaLaunchAttribute at[1];                                                                            \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                 \
+    cfg.attrs = at; cfg.numAttrs = option_get(OPT_D2_PDL) ? 1 : 0;                                        \
+    CK(cudaLaunchKernelEx(&cfg, kern, (const cx<double>*)in, N, (cx<double>*)eta, (cx<double>*)r,         \
+                          (cx<double>*)C, status));                                                       \
   } while (0)
   if (in_is_U) { if (C) QMPS_D2_LAUNCH(true, true); else QMPS_D2_LAUNCH(true, false); }
   else { if (C) QMPS_D2_LAUNCH(false, true); else QMPS_D2_LAUNCH(false, false); }

@@ -1,6 +1,7 @@
 // qmps_b200: generic-D launchers, REAL = double instantiation (own translation unit so
 // the two precisions compile in parallel).
 #include "api_common.cuh"
+#include "launch_envreal.cuh"
 
 using namespace qmps;
 namespace qmps_host {
@@ -24,7 +25,7 @@ int launch_env_generic(EnvParams p, cudaStream_t st) {
   void* ws = nullptr;
   if (!e_in_smem) {
     p.ws_stride = (size_t)n * (n + 1);
-    CK(cudaMallocAsync(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
+    CK(malloc_async(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
     p.ws = ws;
   } else {
     p.ws = nullptr; p.ws_stride = 0;
@@ -36,6 +37,7 @@ int launch_env_generic(EnvParams p, cudaStream_t st) {
 }
 
 template <int MODE> int dispatch_env(const EnvParams& p, cudaStream_t st) {
+  if (env_real_applies(p)) return dispatch_env_real<REAL, MODE>(p, st);
   switch (group_for_n(p.D * p.D)) {
     case 4: return launch_env_generic<4, MODE>(p, st);
     case 16: return launch_env_generic<16, MODE>(p, st);
@@ -58,7 +60,7 @@ template <int G> int launch_fp(FpParams p, cudaStream_t st) {
   void* ws = nullptr;
   if (!h_in_smem) {
     p.ws_stride = (size_t)n * (n + 1);
-    CK(cudaMallocAsync(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
+    CK(malloc_async(&ws, sizeof(cx<REAL>) * p.ws_stride * grid, st));
     p.ws = ws;
   } else { p.ws = nullptr; p.ws_stride = 0; }
   kern<<<grid, block, smem, st>>>(p);

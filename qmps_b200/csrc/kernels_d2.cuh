@@ -66,6 +66,10 @@ env_d2_stream_kernel(const cx<double>* __restrict__ in, int64_t N, cx<double>* _
                      cx<double>* __restrict__ r_out, cx<double>* __restrict__ C_out,
                      int32_t* __restrict__ status_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // programmatic dependent launch: let the next launch on the stream become resident while this
+  // grid drains, and do not touch global memory before the previous grid has completed and
+  // flushed (both are no-ops when the launch does not carry the PDL attribute)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wb = smem_raw + warp * D2_WARP_BYTES;
   cx<double>* stage0 = reinterpret_cast<cx<double>*>(wb);
@@ -75,6 +79,7 @@ env_d2_stream_kernel(const cx<double>* __restrict__ in, int64_t N, cx<double>* _
   const int64_t ntiles = (N + 31) >> 5;
   const int64_t stride = (int64_t)gridDim.x * D2_WARPS;
   int64_t tile = (int64_t)blockIdx.x * D2_WARPS + warp;
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
   if (tile < ntiles) d2_issue_tile<IN_U>(in, N, tile, stage0, lane);
   cp_async_commit();
   int buf = 0;

@@ -1,0 +1,39 @@
+// qmps_b200: launcher of the register-resident real-form environment solver (D = 4, 8),
+// included by the per-precision translation units.
+#pragma once
+#include "api_common.cuh"
+#include "kernels_envreal.cuh"
+
+namespace qmps_host {
+
+template <typename REAL, int D, int MODE>
+int launch_env_real(qmps::EnvParams p, cudaStream_t st) {
+  using namespace qmps;
+  constexpr int n = D * D;
+  const int block = D == 8 ? 64 : 128;
+  const int gpc = block / n;
+  const ErLayout<REAL, D> L = er_layout<REAL, D>(p.d, p.nops, MODE == 1);
+  const size_t smem = L.total * gpc;
+  auto kern = env_real_kernel<REAL, D, MODE>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  const int S = (MODE == 1 && p.nshift > 0) ? p.nshift : 1;
+  const int64_t total = p.N * S;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (total + gpc - 1) / gpc, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// true if the fast path applies
+inline bool env_real_applies(const qmps::EnvParams& p) {
+  return p.assume_lc && (p.D == 4 || p.D == 8) && p.d >= 1 && p.d <= 4;
+}
+
+template <typename REAL, int MODE>
+int dispatch_env_real(const qmps::EnvParams& p, cudaStream_t st) {
+  return p.D == 4 ? launch_env_real<REAL, 4, MODE>(p, st) : launch_env_real<REAL, 8, MODE>(p, st);
+}
+
+}  // namespace qmps_host

@@ -10,11 +10,42 @@
 #include "../../qmps_b200/csrc/ansatz.cuh"
 #include "../../qmps_b200/csrc/generic.cuh"
 #include "../../qmps_b200/csrc/d2.cuh"
+#include "../../qmps_b200/csrc/envreal.cuh"
 
 using namespace qmps;
 typedef cx<double> zc;
 
 static Grp solo() { Grp g; g.lane = 0; g.size = 1; g.mask = 1; g.cta = 0; return g; }
+
+// real-form environment solve (envreal.cuh): the device kernel's row builder, then the same
+// Gauss-Jordan with implicit partial pivoting the kernel runs with one thread per row.
+template <int D> static int env_real_one(const zc* A, int d, zc* r) {
+  constexpr int n = D * D;
+  std::vector<zc> Ap((size_t)d * D * (D + 1));
+  for (int q = 0; q < d * n; ++q) Ap[(q / D) * (D + 1) + q % D] = A[q];
+  std::vector<double> M((size_t)n * (n + 1));
+  for (int e = 0; e < n; ++e) herm_row<double, D>(Ap.data(), D + 1, d, e, &M[(size_t)e * (n + 1)]);
+  std::vector<int> done(n, 0), col_of(n, 0);
+  std::vector<double> piv(n, 1.0), x(n);
+  int bad = 0;
+  for (int k = 0; k < n; ++k) {
+    int who = -1; double best = -1;
+    for (int e = 0; e < n; ++e) if (!done[e] && fabs(M[(size_t)e * (n + 1) + k]) > best) { best = fabs(M[(size_t)e * (n + 1) + k]); who = e; }
+    if (!(best > 1e-13)) bad = 1;
+    const double* prow = &M[(size_t)who * (n + 1)];
+    const double pv = prow[k];
+    for (int e = 0; e < n; ++e) {
+      if (e == who) continue;
+      double f = M[(size_t)e * (n + 1) + k] * (1.0 / pv);
+      for (int j = k + 1; j <= n; ++j) M[(size_t)e * (n + 1) + j] -= f * prow[j];
+    }
+    done[who] = 1; col_of[who] = k; piv[who] = pv;
+  }
+  for (int e = 0; e < n; ++e) x[col_of[e]] = M[(size_t)e * (n + 1) + n] / piv[e];
+  for (int e = 0; e < n; ++e) herm_scatter<double, D>(x.data(), e, r);
+  return bad;
+}
+
 
 extern "C" {
 
@@ -137,6 +168,18 @@ int emu_energy_generic(int D, int64_t N, const double* in, int two_site, const d
     const zc* M = a;
     if (!two_site) { merge_block<double>(g, a, a, 2, 2, D, tmp.data()); M = tmp.data(); }
     energy[p] = energy_from_block<double>(g, M, x.data(), D, (const zc*)hmat, tmp.data() + 4 * n, red.data());
+  }
+  return 0;
+}
+
+int emu_env_real(int d, int D, int64_t N, const double* A, double* r, int32_t* status) {
+  for (int64_t p = 0; p < N; ++p) {
+    const zc* a = (const zc*)A + p * (size_t)d * D * D;
+    zc* out = (zc*)r + p * (size_t)D * D;
+    if (D == 2) status[p] = env_real_one<2>(a, d, out);
+    else if (D == 4) status[p] = env_real_one<4>(a, d, out);
+    else if (D == 8) status[p] = env_real_one<8>(a, d, out);
+    else return -1;
   }
   return 0;
 }

@@ -209,6 +209,24 @@ def test_emu_generic_env_and_fixed_point(emu, D):
             assert np.abs(Em @ vec[k].reshape(-1) - eta[k] * vec[k].reshape(-1)).max() < 1e-11
 
 
+@pytest.mark.parametrize("D", [2, 4, 8])
+def test_emu_env_real_form(emu, D):
+    """envreal.cuh: the Hermitian-basis real system reproduces the oracle's environment, for
+    single-site tensors (d = 2) and for two-site blocks merge(A1, A2) (d = 4)."""
+    N = 6
+    A = np.ascontiguousarray(np.stack([O.unitary_to_tensor(unitary_group.rvs(2 * D, random_state=700 + s)) for s in range(N)]))
+    A2 = np.ascontiguousarray(np.stack([O.unitary_to_tensor(unitary_group.rvs(2 * D, random_state=800 + s)) for s in range(N)]))
+    M = np.ascontiguousarray(np.stack([O.merge(A[k], A2[k]) if D == 2 else
+                                       np.einsum("aik,bkj->abij", A[k], A2[k]).reshape(4, D, D) for k in range(N)]))
+    for d, T in ((2, A), (4, M)):
+        r = np.zeros((N, D, D), complex); st = np.zeros(N, np.int32)
+        assert emu.emu_env_real(d, D, ctypes.c_int64(N), P(T), P(r), P(st)) == 0
+        assert st.sum() == 0
+        for k in range(N):
+            _, r0, _, _ = O.env_exact_parts(T[k])
+            assert np.abs(r[k] - r0).max() < 1e-12
+
+
 def test_emu_ansatz_and_energy(emu):
     from qmps_b200 import represent as R
     rng = np.random.default_rng(3)
