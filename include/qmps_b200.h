@@ -76,7 +76,9 @@ typedef struct qmps_gate_op {
 const char* qmps_version(void);
 const char* qmps_last_error(void);
 /* tuning knobs (no reference counterpart): "d2_pdl" (1: programmatic dependent launch for the
- * D = 2 streaming kernel, default 1), "d2_ctas_per_sm" (0: occupancy limit, default). */
+ * D = 2 streaming kernel, default 1), "d2_ctas_per_sm" (resident CTAs per SM of that kernel, default 1 = measured best; 0: occupancy limit),
+ * "fp16_fast" / "env_real" (1: use the register-resident D = 4 eigenvalue kernel / the real-form
+ * D = 4, 8 direct solver, default 1; 0: the generic shared-memory kernels -- kept for A/B tests). */
 int qmps_set_option(const char* name, int value);
 /* number of visible CUDA devices (0 if none); never fails */
 int qmps_device_count(void);

@@ -2,6 +2,7 @@
 // the two precisions compile in parallel).
 #include "api_common.cuh"
 #include "launch_envreal.cuh"
+#include "kernels_fp16.cuh"
 
 using namespace qmps;
 namespace qmps_host {
@@ -44,6 +45,21 @@ template <int MODE> int dispatch_env(const EnvParams& p, cudaStream_t st) {
     case 128: return launch_env_generic<128, MODE>(p, st);
     default: return launch_env_generic<256, MODE>(p, st);
   }
+}
+
+// D = 4 eigenvalue-only fast path (kernels_fp16.cuh): half a warp per problem
+int launch_fp16(FpParams p, cudaStream_t st) {
+  const Fp16Layout<REAL> L = fp16_layout<REAL>(p.d);
+  const int block = 128, gpc = block / 16;
+  const size_t smem = L.total * gpc;
+  auto kern = fp16_kernel<REAL>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
 }
 
 template <int G> int launch_fp(FpParams p, cudaStream_t st) {
@@ -91,6 +107,7 @@ int env_generic_f64(const EnvParams& p, int mode, cudaStream_t st) {
   return mode == 0 ? dispatch_env<0>(p, st) : dispatch_env<1>(p, st);
 }
 int fixed_point_f64(const FpParams& p, cudaStream_t st) {
+  if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
   switch (group_for_n(p.D * p.D)) {
     case 4: return launch_fp<4>(p, st);
     case 16: return launch_fp<16>(p, st);

@@ -56,20 +56,23 @@ template <typename T> QMPS_HD cx<T> conj(cx<T> a) { return mk<T>(a.re, -a.im); }
 template <typename T> QMPS_HD T norm2(cx<T> a) { return a.re * a.re + a.im * a.im; }
 template <typename T> QMPS_HD T cabs(cx<T> a) { return sqrt(norm2(a)); }
 template <typename T> QMPS_HD T cabs1(cx<T> a) { return fabs(a.re) + fabs(a.im); }
-// acc += a*b
+// fused multiply-add on either precision (one rounding; DFMA / FFMA on the device)
+QMPS_HD double fma_t(double a, double b, double c) { return fma(a, b, c); }
+QMPS_HD float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+// acc += a*b          (4 FMAs, no separate multiplies / adds)
 template <typename T> QMPS_HD void cmad(cx<T>& acc, cx<T> a, cx<T> b) {
-  acc.re += a.re * b.re - a.im * b.im;
-  acc.im += a.re * b.im + a.im * b.re;
+  acc.re = fma_t(-a.im, b.im, fma_t(a.re, b.re, acc.re));
+  acc.im = fma_t(a.im, b.re, fma_t(a.re, b.im, acc.im));
 }
 // acc += a*conj(b)
 template <typename T> QMPS_HD void cmad_c(cx<T>& acc, cx<T> a, cx<T> b) {
-  acc.re += a.re * b.re + a.im * b.im;
-  acc.im += a.im * b.re - a.re * b.im;
+  acc.re = fma_t(a.im, b.im, fma_t(a.re, b.re, acc.re));
+  acc.im = fma_t(-a.re, b.im, fma_t(a.im, b.re, acc.im));
 }
 // acc -= a*b
 template <typename T> QMPS_HD void cmsub(cx<T>& acc, cx<T> a, cx<T> b) {
-  acc.re -= a.re * b.re - a.im * b.im;
-  acc.im -= a.re * b.im + a.im * b.re;
+  acc.re = fma_t(a.im, b.im, fma_t(-a.re, b.re, acc.re));
+  acc.im = fma_t(-a.im, b.re, fma_t(-a.re, b.im, acc.im));
 }
 template <typename T> QMPS_HD cx<T> cinv(cx<T> a) {
   T d = T(1) / norm2(a);

@@ -114,14 +114,15 @@ env_real_kernel(EnvParams p) {
     T mypiv = T(1);
 #pragma unroll
     for (int k = 0; k < n; ++k) {
-      T cand = done ? T(-1) : fabs(m[k]);
-      int who = e;
-#pragma unroll
-      for (int off = (NT < 32 ? NT : 32) >> 1; off > 0; off >>= 1) {
-        const T oc = __shfl_xor_sync(smask, cand, off);
-        const int ow = __shfl_xor_sync(smask, who, off);
-        if (oc > cand || (oc == cand && ow < who)) { cand = oc; who = ow; }
-      }
+      // arg-max of |m[k]| over the unused rows in ONE warp reduction (redux.sync): a 32-bit key =
+      // the top 26 bits of |m[k]| as a float (monotonic in the magnitude) | (63 - row).  Partial
+      // pivoting only needs a pivot within rounding of the largest, not the exact maximum.
+      const T cand_exact = done ? T(-1) : fabs(m[k]);
+      unsigned key = done ? 0u : ((__float_as_uint((float)cand_exact) & ~63u) | (unsigned)(63 - e));
+      if (!done && key < 64u) key = 64u | (unsigned)(63 - e);       // zero column entry: still eligible
+      const unsigned best = __reduce_max_sync(smask, key);
+      int who = 63 - (int)(best & 63u);
+      T cand = __uint_as_float(best & ~63u);
       T* buf = rowbuf + ((k & 1) * NW + wig) * ROWLD;
       T* cb = candbuf + ((k & 1) * NW + wig) * 2;
       if (e == who) {                                         // local winner publishes its row

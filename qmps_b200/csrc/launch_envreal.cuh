@@ -28,7 +28,7 @@ int launch_env_real(qmps::EnvParams p, cudaStream_t st) {
 
 // true if the fast path applies
 inline bool env_real_applies(const qmps::EnvParams& p) {
-  return p.assume_lc && (p.D == 4 || p.D == 8) && p.d >= 1 && p.d <= 4;
+  return option_get(OPT_ENV_REAL) && p.assume_lc && (p.D == 4 || p.D == 8) && p.d >= 1 && p.d <= 4;
 }
 
 template <typename REAL, int MODE>

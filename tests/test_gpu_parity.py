@@ -174,6 +174,55 @@ def test_fixed_point_vs_oracle(env, D, count, left):
             assert np.abs(vec[k] - v0).max() < 1e-9 / gap
 
 
+@pytest.mark.parametrize("left", [False, True])
+@pytest.mark.parametrize("d", [2, 4])
+def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
+    """The register-resident D = 4 kernel (kernels_fp16.cuh, eigenvalue only) against the oracle's
+    dense eig and against the generic shared-memory kernel on the same inputs; d = 4 is the
+    two-site (merged) map of the Loschmidt cost.  An odd batch size leaves half a warp idle."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    count = 101
+    A, Bt = tensors(4, count, 1300 + d, O), tensors(4, count, 1900 + d, O)
+    if d == 4:
+        A = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", A, A[::-1]).reshape(count, 4, 4, 4))
+        Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt[::-1]).reshape(count, 4, 4, 4))
+    Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
+    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+    lib = L.load()
+    lib.qmps_set_option(b"fp16_fast", 0)
+    try:
+        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+        t.cuda.synchronize()
+    finally:
+        lib.qmps_set_option(b"fp16_fast", 1)
+    assert int(fast.status.abs().sum()) == 0
+    assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
+    for k in range(count):
+        x0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])[0]
+        assert abs(abs(fast.eta[k].item()) - abs(x0)) < TOL
+        assert abs(fast.cost[k].item() + np.sqrt(abs(x0))) < TOL
+        w = np.linalg.eigvals(O.transfer_matrix(A[k], Bt[k]))
+        lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
+        assert np.abs(w - lam).min() < 1e-11               # it IS an eigenvalue of E, not just the right modulus
+    # complex64 mode
+    f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
+    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5
+
+
+def test_fixed_point_d4_degenerate_inputs(env):
+    """Edge cases of the QR kernel: identical tensors (eta = 1 exactly known), a product state
+    (rank-one map: 15 zero eigenvalues) and the zero tensor."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(4, 4, 5, O)
+    prod = np.zeros((1, 2, 4, 4), complex); prod[0, 0, 0, 0] = 1.0
+    zero = np.zeros((1, 2, 4, 4), complex)
+    X = t.from_numpy(np.concatenate([A, prod, zero])).cuda()
+    fp = B.fixed_point(X, X, want_vec=False)
+    eta = fp.eta.cpu().numpy()
+    assert np.abs(np.abs(eta[:4]) - 1).max() < 1e-12
+    assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
+
+
 def test_fixed_point_outer_and_broadcast(env):
     t, B, O = env["torch"], env["B"], env["O"]
     A, Bt = tensors(2, 3, 1, O), tensors(2, 5, 2, O)
