@@ -77,9 +77,13 @@ const char* qmps_version(void);
 const char* qmps_last_error(void);
 /* tuning knobs (no reference counterpart): "d2_pdl" (1: programmatic dependent launch for the
  * D = 2 streaming kernel, default 1), "d2_ctas_per_sm" (resident CTAs per SM of that kernel, default 1 = measured best; 0: occupancy limit),
- * "fp16_fast" / "env_real" (1: use the register-resident D = 4 eigenvalue kernel / the real-form
- * D = 4, 8 direct solver, default 1; 0: the generic shared-memory kernels -- kept for A/B tests). */
+ * "fp16_fast" (1: the half-warp register-resident D = 4 eigenvalue kernel; default 0 -- it
+ * measured slower than the generic shared-memory kernel, see profiles/README.md), "env_real"
+ * (1: the real-form register-resident D = 4, 8 direct solver, default 1; 0: generic kernel). */
 int qmps_set_option(const char* name, int value);
+/* diagnostics of the D = 4 QR kernel (complex128) on the current device, after a device
+ * synchronise: out4 = {problems solved, QR sweeps, problems with a forced deflation, 0}. */
+int qmps_debug_counters(unsigned long long* out4, int reset);
 /* number of visible CUDA devices (0 if none); never fails */
 int qmps_device_count(void);
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "qmps_last_error": ([], ctypes.c_char_p),
     "qmps_device_count": ([], _i),
     "qmps_set_option": ([ctypes.c_char_p, _i], _i),
+    "qmps_debug_counters": ([_vp, _i], _i),
     "qmps_unitary_to_tensor": ([_i, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_tensor_to_unitary": ([_i, _i, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_environment_to_unitary": ([_i, _i64, _vp, _vp, _i, _vp], _i),

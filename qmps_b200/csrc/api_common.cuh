@@ -125,6 +125,7 @@ int env_generic_f64(const qmps::EnvParams& p, int mode, cudaStream_t st);
 int env_generic_f32(const qmps::EnvParams& p, int mode, cudaStream_t st);
 int fixed_point_f64(const qmps::FpParams& p, cudaStream_t st);
 int fixed_point_f32(const qmps::FpParams& p, cudaStream_t st);
+int fp16_debug_f64(unsigned long long* out, int reset);
 int ansatz_f64(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
 int ansatz_f32(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
 // capi_d2.cu

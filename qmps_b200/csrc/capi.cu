@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 1 /* fp16_fast */, 1 /* env_real */, 0, 0, 0, 0};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 0, 0, 0, 0};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
@@ -121,6 +121,10 @@ int qmps_set_option(const char* name, int value) {
   if (!strcmp(name, "fp16_fast")) { g_options[OPT_FP16_FAST] = value; return 0; }
   if (!strcmp(name, "env_real")) { g_options[OPT_ENV_REAL] = value; return 0; }
   return fail(QMPS_ERR_ARG, std::string("set_option: unknown option ") + name);
+}
+int qmps_debug_counters(unsigned long long* out4, int reset) {
+  if (!out4) return fail(QMPS_ERR_ARG, "debug_counters: null output");
+  return fp16_debug_f64(out4, reset);
 }
 int qmps_device_count(void) {
   int n = 0;

@@ -106,6 +106,15 @@ int launch_ansatz(const GateOp* dops, int nops, int nq, int64_t N, int P, const 
 int env_generic_f64(const EnvParams& p, int mode, cudaStream_t st) {
   return mode == 0 ? dispatch_env<0>(p, st) : dispatch_env<1>(p, st);
 }
+int fp16_debug_f64(unsigned long long* out, int reset) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out, g_fp16_dbg, 4 * sizeof(unsigned long long)));
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyToSymbol(g_fp16_dbg, z, sizeof(z)));
+  }
+  return 0;
+}
 int fixed_point_f64(const FpParams& p, cudaStream_t st) {
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
   switch (group_for_n(p.D * p.D)) {

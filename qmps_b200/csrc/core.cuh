@@ -88,6 +88,22 @@ template <typename T> QMPS_HD cx<T> csqrt(cx<T> z) {
   return mk<T>(fabs(b), z.im < T(0) ? -a : a);
 }
 
+// 1/sqrt(x): one MUFU + Newton steps on the device instead of a square root AND a division
+QMPS_HD double rsqrt_hd(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+QMPS_HD float rsqrt_hd(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
 // ---- the cooperating group -------------------------------------------------------
 struct Grp {
   int lane;       // 0 .. size-1
@@ -275,10 +291,11 @@ QMPS_HDN int hqr_eigenvalues(const Grp& g, cx<T>* H, int ld, int n, cx<T>* w, cx
       // -- left rotations: R = G_en ... G_{l+1} (H - sh)
       for (int i = l + 1; i <= en; ++i) {
         cx<T> f = H[(i - 1) * ld + (i - 1)], gg = H[i * ld + (i - 1)];
-        T nr = sqrt(norm2(f) + norm2(gg));
+        const T nr2 = norm2(f) + norm2(gg);
+        T nr = T(0);
         cx<T> c, s;
-        if (nr == T(0)) { c = mk<T>(1, 0); s = mk<T>(0, 0); }
-        else { T inr = T(1) / nr; c = f * inr; s = gg * inr; }
+        if (nr2 == T(0)) { c = mk<T>(1, 0); s = mk<T>(0, 0); }
+        else { const T inr = rsqrt_hd(nr2); nr = nr2 * inr; c = f * inr; s = gg * inr; }
         if (g.lane == 0) { rc[i] = c; rs[i] = s; rn[i] = nr; }
         // columns j >= i only: column i-1 is fixed up after the loop (nobody reads
         // rows i-1,i of column i-1 again during the left phase)

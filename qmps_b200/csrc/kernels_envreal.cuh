@@ -136,6 +136,7 @@ env_real_kernel(EnvParams p) {
         cb[0] = cand;
         cb[1] = T(who);
       }
+      if (NW > 1 && best == 0u && (e & 31) == 0) cb[0] = T(-1);   // this warp has no unused row left
       g.sync();
       int gwho = who;
       const T* prow = buf;

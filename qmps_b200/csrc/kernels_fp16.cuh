@@ -22,6 +22,9 @@ namespace qmps {
 
 constexpr int F16_N = 16, F16_LD = 17;
 
+// diagnostics (qmps_debug_counter): [0] problems solved, [1] QR sweeps, [2] forced deflations
+__device__ unsigned long long g_fp16_dbg[4];
+
 template <typename T> struct Fp16Layout { size_t S, rot, vbuf, ubuf, A, B, total; };
 template <typename T> QMPS_HD Fp16Layout<T> fp16_layout(int d) {
   Fp16Layout<T> L;
@@ -214,7 +217,7 @@ fp16_kernel(FpParams p) {
     __syncwarp();
 
     // ---- shifted QR, all eigenvalues; keep the one of largest modulus
-    int en = F16_N - 1, its = 0, fail = 0;
+    int en = F16_N - 1, its = 0, fail = 0, sweeps = 0;
     T best2 = T(-1);
     cx<T> best = mk<T>(0, 0);
     for (;;) {
@@ -269,8 +272,12 @@ fp16_kernel(FpParams p) {
       else fp16_sweep<T, 3>(h, ln, lw, enw, sigma, S, rot);
       __syncwarp();
       ++its;
+      if (en >= 1) ++sweeps;
     }
     if (live && ln == 0) {
+      atomicAdd(&g_fp16_dbg[0], 1ull);
+      atomicAdd(&g_fp16_dbg[1], (unsigned long long)sweeps);
+      if (fail) atomicAdd(&g_fp16_dbg[2], 1ull);
       const T a2 = norm2(best);
       if (p.eta) reinterpret_cast<cx<T>*>(p.eta)[pid] = best;
       if (p.cost) reinterpret_cast<T*>(p.cost)[pid] = -sqrt(sqrt(a2));

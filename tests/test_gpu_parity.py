@@ -187,14 +187,15 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
         A = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", A, A[::-1]).reshape(count, 4, 4, 4))
         Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt[::-1]).reshape(count, 4, 4, 4))
     Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
-    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
     lib = L.load()
-    lib.qmps_set_option(b"fp16_fast", 0)
+    slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)      # default: generic shared-memory kernel
+    lib.qmps_set_option(b"fp16_fast", 1)
     try:
-        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+        fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+        f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
         t.cuda.synchronize()
     finally:
-        lib.qmps_set_option(b"fp16_fast", 1)
+        lib.qmps_set_option(b"fp16_fast", 0)
     assert int(fast.status.abs().sum()) == 0
     assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
     for k in range(count):
@@ -204,9 +205,7 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
         w = np.linalg.eigvals(O.transfer_matrix(A[k], Bt[k]))
         lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
         assert np.abs(w - lam).min() < 1e-11               # it IS an eigenvalue of E, not just the right modulus
-    # complex64 mode
-    f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
-    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5
+    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5      # complex64 mode
 
 
 def test_fixed_point_d4_degenerate_inputs(env):
@@ -217,10 +216,16 @@ def test_fixed_point_d4_degenerate_inputs(env):
     prod = np.zeros((1, 2, 4, 4), complex); prod[0, 0, 0, 0] = 1.0
     zero = np.zeros((1, 2, 4, 4), complex)
     X = t.from_numpy(np.concatenate([A, prod, zero])).cuda()
-    fp = B.fixed_point(X, X, want_vec=False)
-    eta = fp.eta.cpu().numpy()
-    assert np.abs(np.abs(eta[:4]) - 1).max() < 1e-12
-    assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
+    lib = env["L"].load()
+    for fast in (0, 1):
+        lib.qmps_set_option(b"fp16_fast", fast)
+        try:
+            fp = B.fixed_point(X, X, want_vec=False)
+            eta = fp.eta.cpu().numpy()
+        finally:
+            lib.qmps_set_option(b"fp16_fast", 0)
+        assert np.abs(np.abs(eta[:4]) - 1).max() < 1e-12
+        assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
 
 
 def test_fixed_point_outer_and_broadcast(env):
