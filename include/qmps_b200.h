@@ -179,6 +179,16 @@ int qmps_loschmidt_rate(int64_t NT, const double* t, double g0, double g1, doubl
 int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K,
                   void* rayleigh, int dtype, void* stream);
 
+/* cfg 5  building block of the complex64 power method: batched complex product on the tcgen05
+ *     tensor cores (kind::tf32, 3xTF32 split = FP32-grade results),
+ *         C[b] = sum_t X[b][t] . op(Y[b][t]),   op = transpose (conj_y = 0) / conjugate transpose (1)
+ *     X [batch][nsum][M][K], Y [batch][nsum][N][K] (both K-major), C [batch][M][N], complex64,
+ *     DEVICE pointers; M and N multiples of 64, K a multiple of 32 (else QMPS_ERR_UNSUPPORTED).
+ *     Stage 1 (A_s . r) and stage 2 (sum_s T_s . B_s^dagger) of qmps_tm_power are two calls of the
+ *     same kernel (qmps.ipynb cells 29-32). */
+int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y,
+                      int conj_y, void* C, void* stream);
+
 /* (e)  local part of the final cost reduction: (min cost, argmin + index_offset) of a
  *     DEVICE array, written to DEVICE best_cost[1] / best_index[1]; the cross-rank
  *     step is one NCCL all-gather of 16 bytes per rank (qmps_b200/dist.py). */

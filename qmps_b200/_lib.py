@@ -48,6 +48,7 @@ SIGNATURES = {
     "qmps_energy_tensor": ([_i, _i64, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_rotosolve_fit": ([_i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "qmps_tm_power": ([_i, _i, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp], _i),
+    "qmps_cgemm_c64_tc": ([_i64, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
     "qmps_argmin": ([_i64, _vp, _i64, _vp, _vp, _vp], _i),
     "qmps_loschmidt_rate": ([_i64, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp], _i),
 }

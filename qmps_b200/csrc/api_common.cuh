@@ -23,7 +23,7 @@ inline int fail(int code, const std::string& msg) { last_error() = msg; return c
   } while (0)
 
 // tuning knobs (qmps_set_option); defaults are the measured best
-enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_COUNT = 8 };
+enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_TC_POWER = 4, OPT_TC_PERSISTENT = 5, OPT_COUNT = 8 };
 int option_get(int key);                          // defined in capi.cu
 
 inline int sm_count() {
@@ -133,5 +133,9 @@ int env_d2(int64_t N, const void* in, int in_is_U, void* eta, void* r, void* C, 
 int energy_d2_theta(const qmps::GateOp* dops, int nops, int64_t N, int P, const double* theta, const void* hmat, int coord,
                     const double* dshifts, int nshift, void* energy, int32_t* status, int dtype, cudaStream_t st);
 int d2_max_ops();
+// capi_tc.cu (tcgen05, complex64)
+bool tm_power_tc_applies(int d, int D, int64_t N);
+int tm_power_tc(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh, cudaStream_t st);
+int cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C, cudaStream_t st);
 
 }  // namespace qmps_host

@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 0, 0, 0, 0};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
@@ -120,6 +120,8 @@ int qmps_set_option(const char* name, int value) {
   if (!strcmp(name, "d2_ctas_per_sm")) { g_options[OPT_D2_CTAS_PER_SM] = value; return 0; }
   if (!strcmp(name, "fp16_fast")) { g_options[OPT_FP16_FAST] = value; return 0; }
   if (!strcmp(name, "env_real")) { g_options[OPT_ENV_REAL] = value; return 0; }
+  if (!strcmp(name, "tc_power")) { g_options[OPT_TC_POWER] = value; return 0; }
+  if (!strcmp(name, "tc_persistent")) { g_options[OPT_TC_PERSISTENT] = value; return 0; }
   return fail(QMPS_ERR_ARG, std::string("set_option: unknown option ") + name);
 }
 int qmps_debug_counters(unsigned long long* out4, int reset) {
@@ -313,8 +315,15 @@ int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r
   if (d < 1 || D < 1 || N < 0 || K < 0 || (N && (!A || !B || !r_io))) return fail(QMPS_ERR_ARG, "tm_power: bad arguments");
   if (N * d > 65535) return fail(QMPS_ERR_UNSUPPORTED, "tm_power: N*d > 65535 (split the batch)");
   if (dtype == QMPS_C128) return tm_power_f64(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
+  if (dtype == QMPS_C64 && tm_power_tc_applies(d, D, N)) return tm_power_tc(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
   if (dtype == QMPS_C64) return tm_power_impl<float>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
   return fail(QMPS_ERR_ARG, "tm_power: bad dtype");
+}
+
+int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C,
+                      void* stream) {
+  if (batch < 0 || nsum < 1 || (batch && (!X || !Y || !C))) return fail(QMPS_ERR_ARG, "cgemm_c64_tc: bad arguments");
+  return cgemm_c64_tc(batch, nsum, M, N, K, X, Y, conj_y, C, (cudaStream_t)stream);
 }
 
 int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* best_cost, int64_t* best_index,
