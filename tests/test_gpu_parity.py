@@ -485,6 +485,87 @@ def test_tm_power_complex64(env):
         assert abs(ray[k].item() - q0) < 1e-5
 
 
+# ---------------------------------------------------------------- cfg 5, complex64 on tcgen05
+def _cgemm_tc(env, X, Y, conj):
+    t, L = env["torch"], env["L"]
+    batch, nsum, M, K = X.shape
+    N = Y.shape[2]
+    Xd, Yd = t.from_numpy(X).cuda(), t.from_numpy(Y).cuda()
+    C = t.empty((batch, M, N), dtype=t.complex64, device="cuda")
+    L.check(L.load().qmps_cgemm_c64_tc(batch, nsum, M, N, K, Xd.data_ptr(), Yd.data_ptr(), int(conj), C.data_ptr(),
+                                       t.cuda.current_stream().cuda_stream), "cgemm_c64_tc")
+    t.cuda.synchronize()
+    return C.cpu().numpy()
+
+
+@pytest.mark.parametrize("persistent", [1, 0])
+@pytest.mark.parametrize("shape", [(1, 1, 64, 64, 32, 0), (1, 1, 64, 64, 32, 1), (2, 2, 64, 64, 128, 1),
+                                   (3, 1, 128, 192, 96, 0), (40, 2, 128, 128, 64, 1), (700, 1, 64, 64, 64, 0)])
+def test_cgemm_tc_vs_numpy(env, shape, persistent):
+    """The tcgen05 3xTF32 tile kernel against a float64 numpy product: single slab, multi-slab ring
+    wrap-around, summands, several tiles per matrix, more tiles than SMs (persistent loop,
+    both TMEM accumulators), both op(Y)."""
+    batch, nsum, M, N, K, conj = shape
+    env["L"].load().qmps_set_option(b"tc_persistent", persistent)
+    try:
+        rng = np.random.default_rng(batch * 1000 + K + conj)
+        X = (rng.normal(size=(batch, nsum, M, K)) + 1j * rng.normal(size=(batch, nsum, M, K))).astype(np.complex64)
+        Y = (rng.normal(size=(batch, nsum, N, K)) + 1j * rng.normal(size=(batch, nsum, N, K))).astype(np.complex64)
+        ref = np.einsum("btmk,btnk->bmn", X.astype(np.complex128), (Y.conj() if conj else Y).astype(np.complex128))
+        got = _cgemm_tc(env, X, Y, conj)
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5          # complex64 tolerance of the north star
+    finally:
+        env["L"].load().qmps_set_option(b"tc_persistent", 1)
+
+
+def test_cgemm_tc_linearity_and_edge_cases(env):
+    """Size-independent properties at the cfg-5 size (D = 256): C(X1 + X2, Y) = C(X1, Y) + C(X2, Y),
+    C(X, Y)^H = C(Y, X) for op = conjugate transpose; empty batch; unsupported shapes are refused."""
+    t, L = env["torch"], env["L"]
+    rng = np.random.default_rng(5)
+    mk = lambda *s: (rng.normal(size=s) + 1j * rng.normal(size=s)).astype(np.complex64)
+    X1, X2, Y = mk(4, 2, 256, 256), mk(4, 2, 256, 256), mk(4, 2, 256, 256)
+    c1, c2, c12 = _cgemm_tc(env, X1, Y, 1), _cgemm_tc(env, X2, Y, 1), _cgemm_tc(env, X1 + X2, Y, 1)
+    scale = np.abs(c12).max()
+    assert np.abs(c12 - (c1 + c2)).max() / scale < 1e-5
+    assert np.abs(_cgemm_tc(env, Y, X1, 1) - np.conj(np.swapaxes(c1, -1, -2))).max() / scale < 1e-5
+    lib = L.load()
+    assert lib.qmps_cgemm_c64_tc(0, 1, 64, 64, 32, None, None, 0, None, None) == 0
+    z = t.zeros((1, 1, 96, 32), dtype=t.complex64, device="cuda")
+    assert lib.qmps_cgemm_c64_tc(1, 1, 96, 64, 32, z.data_ptr(), z.data_ptr(), 0, z.data_ptr(), None) != 0   # M % 64
+
+
+@pytest.mark.parametrize("D,cnt,K", [(64, 3, 8), (128, 2, 5), (256, 2, 8), (64, 2, 0), (64, 2, 1)])
+def test_tm_power_complex64_tcgen05_vs_oracle(env, D, cnt, K):
+    """cfg 5 in complex64 runs on tcgen05 for D % 64 == 0: same K steps as the oracle, 1e-5."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A, Bt = tensors(D, cnt, 1400 + D, O), tensors(D, cnt, 1500 + D, O)
+    rng = np.random.default_rng(D + K)
+    r0 = rng.normal(size=(cnt, D, D)) + 1j * rng.normal(size=(cnt, D, D))
+    r0 /= np.linalg.norm(r0, axis=(1, 2), keepdims=True)
+    c64 = lambda x: t.from_numpy(x).cuda().to(t.complex64)
+    for start in (None, r0):
+        r, ray = B.tm_power(c64(A), c64(Bt), K=K, r0=None if start is None else c64(start))
+        for k in range(cnt):
+            ref_r, ref_q = O.power_method(A[k], Bt[k], K, None if start is None else start[k])
+            assert np.abs(r[k].cpu().numpy() - ref_r).max() < 1e-5
+            assert abs(ray[k].item() - ref_q) < 1e-5
+
+
+def test_tm_power_complex64_tcgen05_matches_simt_path(env):
+    """The tensor-core path and the SIMT complex64 path agree (same inputs, option toggled)."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    A, Bt = tensors(64, 4, 1464, O), tensors(64, 4, 1564, O)
+    c64 = lambda x: t.from_numpy(x).cuda().to(t.complex64)
+    r1, q1 = B.tm_power(c64(A), c64(Bt), K=16)
+    L.load().qmps_set_option(b"tc_power", 0)
+    try:
+        r2, q2 = B.tm_power(c64(A), c64(Bt), K=16)
+    finally:
+        L.load().qmps_set_option(b"tc_power", 1)
+    assert (r1 - r2).abs().max().item() < 1e-5 and (q1 - q2).abs().max().item() < 1e-5
+
+
 def test_argmin(env):
     t, B = env["torch"], env["B"]
     rng = np.random.default_rng(0)

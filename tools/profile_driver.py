@@ -63,6 +63,12 @@ def main():
             Bt = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float64, device=dev, generator=g)) / np.sqrt(2 * D)
             for _ in range(args.reps):
                 B.tm_power(A, Bt, 2)
+    for tag, D, N in (("tc64", 64, 512), ("tc256", 256, 32)):      # complex64: tcgen05 path
+        if tag in what:
+            A = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float32, device=dev, generator=g)) / np.sqrt(2 * D)
+            Bt = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float32, device=dev, generator=g)) / np.sqrt(2 * D)
+            for _ in range(args.reps):
+                B.tm_power(A, Bt, 2)
     torch.cuda.synchronize()
     print("profile_driver done:", what)
 
