@@ -189,6 +189,45 @@ int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r
 int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y,
                       int conj_y, void* C, void* stream);
 
+/* ---- canonical forms and local expectation values (xmps' iMPS methods as the
+ *      reference's loops call them; xmps is not vendored, so the gauge is this build's documented
+ *      Cholesky gauge -- every quantity the call sites consume is gauge invariant) ---------------- */
+
+/* iMPS([A]).left_canonicalise() (call sites qmps/time_evolve_tools.py:85-86,
+ *     qmps/loschmidts/time_evo.py:76,143; scripts/loschmidt.py:210,368):
+ *     A [N][d][D][D] (any normalisable tensor) -> AL = L A L^-1 / sqrt(eta) with
+ *     sum_s AL_s^dagger AL_s = 1, where l = L^dagger L is the left fixed point of E_AA
+ *     (L upper triangular, positive diagonal, tr(l) = D).
+ *     out: AL [N][d][D][D]; optional eta [N] complex, L [N][D][D], status [N]
+ *     (QMPS_ST_NOT_PD when l is not positive definite, QMPS_ST_NO_CONVERGE from the eigen-solve). */
+int qmps_left_canonicalise(int d, int D, int64_t N, const void* A, void* AL, void* eta, void* L,
+                           int32_t* status, int dtype, void* stream);
+
+/* iMPS([A]).mixed() -> (AL, AR, C) (qmps/tools.py:184-186 get_env_exact_alternative,
+ *     qmps/ground_state.py:287, tests/test_represent.py:18-31):
+ *     AL as above (assume_left_canonical = 1: AL = A, no eigen-solve), C lower Cholesky factor of the
+ *     trace-1 right fixed point r of E_ALAL (r = C C^dagger), AR = C^-1 AL C, so that
+ *     Map(AL,AL): right r, left 1;  Map(AR,AR): right 1, left C^dagger C   (test_represent.py:23-31).
+ *     All outputs optional: AL, AR [N][d][D][D], C [N][D][D], eta [N], status [N]. */
+int qmps_mixed_canonical(int d, int D, int64_t N, const void* A, int assume_left_canonical, void* AL,
+                         void* AR, void* C, void* eta, int32_t* status, int dtype, void* stream);
+
+/* building block of the two above: A' = L A L^-1 / sqrt|eta| with X = l Hermitian PD, l = L^dagger L
+ *     (x_kind 0; G_out = L), or A' = C^-1 A C with X = C lower triangular (x_kind 1).
+ *     eta, G_out, status optional. */
+int qmps_gauge_transform(int d, int D, int64_t N, const void* A, const void* X, int x_kind,
+                         const void* eta, void* A_out, void* G_out, int32_t* status, int dtype,
+                         void* stream);
+
+/* iMPS([A]).Es(ops) / .E(op) (qmps/loschmidts/time_evo.py:144, scripts/loschmidt.py:369,
+ *     tests/test_represent.py:37): single-site expectation values
+ *       out[n][o] = sum_st ops[o][s][t] tr(l A_t r A_s^dagger) / (eta tr(l r)).
+ *     A [N][d][D][D], r [N][D][D] right fixed point; lvec (optional) = `vec` of
+ *     qmps_fixed_point(left = 1) and eta (optional) for a tensor that is not left-canonical;
+ *     lvec = eta = NULL: A left-canonical, tr r = 1.  ops DEVICE [nops][d][d]; out [N][nops] complex. */
+int qmps_expectation(int d, int D, int64_t N, const void* A, const void* r, const void* lvec,
+                     const void* eta, int nops, const void* ops, void* out, int dtype, void* stream);
+
 /* (e)  local part of the final cost reduction: (min cost, argmin + index_offset) of a
  *     DEVICE array, written to DEVICE best_cost[1] / best_index[1]; the cross-rank
  *     step is one NCCL all-gather of 16 bytes per rank (qmps_b200/dist.py). */

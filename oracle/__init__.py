@@ -29,7 +29,7 @@ Parity pinning status (see DESIGN.md section "Oracle"):
 * PARITY UNPINNED: everything whose arithmetic lives in the un-vendored,
   un-pinned third-party packages ``xmps`` (``TransferMatrix.eigs``,
   ``Map.right_fixed_point``/``left_fixed_point``, ``iMPS.left_canonicalise``,
-  ``iMPS.overlap``) and ``cirq`` (gate matrices, circuit simulation).  Those
+  ``iMPS.overlap``, ``iMPS.mixed``, ``iMPS.Es`` -- ``oracle/canonical.py``) and ``cirq`` (gate matrices, circuit simulation).  Those
   are restated from their published definitions and anchored on the
   reference's call sites (eigen-equation, Hermitian PD ``r``, unit-Frobenius
   fixed points, big-endian qubit order) -- see SURVEY.md A.2 / A.5.
@@ -38,3 +38,4 @@ Parity pinning status (see DESIGN.md section "Oracle"):
 from .tensors import *      # noqa: F401,F403
 from .gates import *        # noqa: F401,F403
 from .costs import *        # noqa: F401,F403
+from .canonical import *    # noqa: F401,F403

@@ -49,6 +49,10 @@ SIGNATURES = {
     "qmps_rotosolve_fit": ([_i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "qmps_tm_power": ([_i, _i, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp], _i),
     "qmps_cgemm_c64_tc": ([_i64, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
+    "qmps_left_canonicalise": ([_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_mixed_canonical": ([_i, _i, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_gauge_transform": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_expectation": ([_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp], _i),
     "qmps_argmin": ([_i64, _vp, _i64, _vp, _vp, _vp], _i),
     "qmps_loschmidt_rate": ([_i64, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp], _i),
 }

@@ -18,6 +18,8 @@ from . import _lib as L
 EnvResult = namedtuple("EnvResult", "eta r C status")
 FixedPoint = namedtuple("FixedPoint", "eta vec cost echo fid status")
 RotoFit = namedtuple("RotoFit", "theta_star fit")
+Canonical = namedtuple("Canonical", "AL eta L status")
+Mixed = namedtuple("Mixed", "AL AR C eta status")
 
 _CDT = {torch.complex128: L.C128, torch.complex64: L.C64}
 _RDT = {torch.complex128: torch.float64, torch.complex64: torch.float32}
@@ -293,6 +295,92 @@ def overlap_theta(program, theta1, theta2, dtype=torch.complex128):
     A = ansatz_tensors(program, theta1, dtype=dtype)
     B = ansatz_tensors(program, theta2, dtype=dtype)
     return fixed_point(A, B, want_vec=True)
+
+
+# ---- canonical forms and local expectation values ----------------------------
+def left_canonicalise(A, want_L=False, want_status=True):
+    """``iMPS([A]).left_canonicalise()`` for a batch A[N, d, D, D] of normalisable tensors
+    (call sites qmps/time_evolve_tools.py:85-86, qmps/loschmidts/time_evo.py:76,143):
+    AL = L A L^-1 / sqrt(eta), sum_s AL_s^dagger AL_s = 1.  Returns ``Canonical(AL, eta, L, status)``."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    N, d, D, _ = A.shape
+    AL = torch.empty_like(A)
+    eta = torch.empty((N,), dtype=A.dtype, device=A.device)
+    Lm = torch.empty((N, D, D), dtype=A.dtype, device=A.device) if want_L else None
+    st = torch.empty((N,), dtype=torch.int32, device=A.device) if want_status else None
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_left_canonicalise(d, D, N, _p(A), _p(AL), _p(eta), _p(Lm), _p(st), _dt(A), _stream()),
+                "left_canonicalise")
+    return Canonical(AL, eta, Lm, st)
+
+
+def mixed_canonical(A, assume_left_canonical=False, want_status=True):
+    """``iMPS([A]).mixed() -> (AL, AR, C)`` for a batch (qmps/tools.py:184-186,
+    tests/test_represent.py:18-31).  Returns ``Mixed(AL, AR, C, eta, status)``."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    N, d, D, _ = A.shape
+    AL = A if assume_left_canonical else torch.empty_like(A)
+    AR = torch.empty_like(A)
+    C = torch.empty((N, D, D), dtype=A.dtype, device=A.device)
+    eta = torch.empty((N,), dtype=A.dtype, device=A.device)
+    st = torch.empty((N,), dtype=torch.int32, device=A.device) if want_status else None
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_mixed_canonical(d, D, N, _p(A), int(bool(assume_left_canonical)),
+                                              None if assume_left_canonical else _p(AL), _p(AR), _p(C), _p(eta), _p(st),
+                                              _dt(A), _stream()), "mixed_canonical")
+    return Mixed(AL, AR, C, eta, st)
+
+
+def gauge_transform(A, X, kind, eta=None):
+    """``kind='left'``: X = l (Hermitian PD), A' = L A L^-1 / sqrt|eta| with l = L^dagger L;
+    ``kind='right'``: X = C lower triangular, A' = C^-1 A C."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    X = _cdev(X, A.dtype, A.device)
+    N, d, D, _ = A.shape
+    eta = None if eta is None else _cdev(eta, A.dtype, A.device)
+    out = torch.empty_like(A)
+    st = torch.empty((N,), dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_gauge_transform(d, D, N, _p(A), _p(X), {"left": 0, "right": 1}[kind], _p(eta), _p(out),
+                                              None, _p(st), _dt(A), _stream()), "gauge_transform")
+    return out, st
+
+
+def expectation_values(A, ops, r=None, lvec=None, eta=None, assume_left_canonical=True):
+    """``iMPS([A]).Es(ops)`` for a batch (qmps/loschmidts/time_evo.py:144, tests/test_represent.py:37):
+    out[n, o] = <ops[o]> on site tensors A[N, d, D, D]; ops [nops, d, d].
+
+    ``assume_left_canonical`` (tensors that come from a unitary): the trace-1 right environment
+    is solved here unless ``r`` is given.  Otherwise the right / left leading eigenvectors of
+    E_AA are computed (or taken from ``r``, ``lvec``, ``eta``) and the general formula is used."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    ops = _cdev(np.asarray(ops) if not isinstance(ops, torch.Tensor) else ops, A.dtype, A.device)
+    N, d, D, _ = A.shape
+    if ops.dim() == 2:
+        ops = ops[None]
+    if assume_left_canonical:
+        if r is None:
+            r = env_exact(A=A, want_eta=False, want_C=False, want_status=False).r
+        lvec = eta = None
+    else:
+        if r is None or eta is None:
+            fp = fixed_point(A, A, want_costs=False, want_status=False)
+            r, eta = fp.vec, fp.eta
+        if lvec is None:
+            lvec = fixed_point(A, A, left=True, want_costs=False, want_status=False).vec
+        lvec, eta = _cdev(lvec, A.dtype, A.device), _cdev(eta, A.dtype, A.device)
+    r = _cdev(r, A.dtype, A.device)
+    out = torch.empty((N, ops.shape[0]), dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_expectation(d, D, N, _p(A), _p(r), _p(lvec), _p(eta), ops.shape[0], _p(ops), _p(out),
+                                          _dt(A), _stream()), "expectation")
+    return out
+
+
+def overlap(A, B):
+    """``iMPS.overlap`` as the reference plots it: per-site fidelity |eta(E_AB)|^2
+    for batches of tensors (broadcast like ``fixed_point``)."""
+    return fixed_point(A, B, want_vec=False, want_status=False).fid
 
 
 # ---- a13 -----------------------------------------------------------------------------

@@ -160,10 +160,15 @@ def get_env_exact(U):
 
 
 def get_env_exact_alternative(U):
-    """qmps/tools.py:184-186 goes through ``iMPS.mixed()``; for a unitary-derived
-    (left-canonical) tensor its C satisfies C C^dagger = r up to a unitary gauge, and the
-    lower-triangular representative is the Cholesky factor used above."""
-    return get_env_exact(U)
+    """qmps/tools.py:184-186: ``AL, AR, C = iMPS([unitary_to_tensor(U)]).mixed()`` ->
+    ``environment_to_unitary(C)``.  The tensor of a unitary is already left-canonical; C is taken
+    in the lower-triangular (Cholesky) gauge, so this equals ``get_env_exact(U)``."""
+    from . import batched, _lib
+    A = unitary_to_tensor(np.asarray(U, dtype=np.complex128))
+    res = batched.mixed_canonical(np.ascontiguousarray(A)[None], assume_left_canonical=True)
+    if int(res.status.cpu()[0]) != _lib.ST_OK:
+        raise LinAlgError("environment is not positive definite (Cholesky failed)")
+    return environment_to_unitary(res.C.cpu().numpy()[0])
 
 
 # ---- host-side drivers (keep their signatures; the cost they call is on the GPU) ------

@@ -11,6 +11,7 @@
 #include "../../qmps_b200/csrc/generic.cuh"
 #include "../../qmps_b200/csrc/d2.cuh"
 #include "../../qmps_b200/csrc/envreal.cuh"
+#include "../../qmps_b200/csrc/canon.cuh"
 
 using namespace qmps;
 typedef cx<double> zc;
@@ -181,6 +182,33 @@ int emu_env_real(int d, int D, int64_t N, const double* A, double* r, int32_t* s
     else if (D == 8) status[p] = env_real_one<8>(a, d, out);
     else return -1;
   }
+  return 0;
+}
+
+// canon.cuh: gauge transform (x_kind 0: X = l -> L A L^-1 * scale; 1: X = C -> C^-1 A C)
+int emu_gauge(int d, int D, int64_t N, const double* A, const double* X, int x_kind, const double* scale, double* out,
+              double* gout, int32_t* status) {
+  const int n = D * D;
+  std::vector<zc> sA((size_t)d * n), sG(n), sGi(n), sT(n);
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p)
+    status[p] = gauge_problem<double>(g, (const zc*)A + p * (size_t)d * n, (const zc*)X + p * (size_t)n, x_kind,
+                                      scale ? scale[p] : 1.0, d, D, sA.data(), sG.data(), sGi.data(), sT.data(),
+                                      (zc*)out + p * (size_t)d * n, gout ? (zc*)gout + p * (size_t)n : nullptr);
+  return 0;
+}
+
+// canon.cuh: single-site expectation values; lvec / eta may be null (left-canonical A, tr r = 1)
+int emu_expect(int d, int D, int64_t N, const double* A, const double* r, const double* lvec, const double* eta,
+               int nops, const double* ops, double* out) {
+  const int n = D * D;
+  std::vector<zc> sA((size_t)d * n), sR(n), sL(n), sP((size_t)d * n), sQ((size_t)d * d * D), sM(d * d);
+  Grp g = solo();
+  for (int64_t p = 0; p < N; ++p)
+    expect_problem<double>(g, (const zc*)A + p * (size_t)d * n, (const zc*)r + p * (size_t)n,
+                           lvec ? (const zc*)lvec + p * (size_t)n : nullptr, eta ? (const zc*)eta + p : nullptr,
+                           (const zc*)ops, nops, d, D, sA.data(), sR.data(), sL.data(), sP.data(), sQ.data(), sM.data(),
+                           (zc*)out + p * (size_t)nops);
   return 0;
 }
 

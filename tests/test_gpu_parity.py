@@ -646,3 +646,117 @@ def test_env_exact_host_entry_point(env):
         _, r0, C0, _ = O.env_exact_parts(A[k])
         assert np.abs(r[k] - r0).max() < 1e-10 and np.abs(r[k + 50 * 99] - r0).max() < 1e-10
         assert np.abs(C[k] - C0).max() < 1e-9
+
+
+# ---------------------------------------------------------------- canonical forms, Es, overlap
+_PAULIS = np.array([[[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]], dtype=complex)
+
+
+def _random_tensors(d, D, count, seed):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(rng.normal(size=(count, d, D, D)) + 1j * rng.normal(size=(count, d, D, D)))
+
+
+@pytest.mark.parametrize("d,D,count", [(2, 2, 133), (2, 4, 40), (4, 4, 9), (2, 8, 6), (2, 16, 2)])
+def test_left_canonicalise_and_mixed_vs_oracle(env, d, D, count):
+    """iMPS([A]).left_canonicalise() / .mixed() on random NON-canonical tensors (ragged batch sizes)
+    against oracle/canonical.py, plus the properties of the reference's tests/test_represent.py:23-31."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = _random_tensors(d, D, count, 900 + D + d)
+    lc = B.left_canonicalise(t.from_numpy(A).cuda(), want_L=True)
+    mx = B.mixed_canonical(t.from_numpy(A).cuda())
+    assert int(lc.status.abs().sum()) == 0 and int(mx.status.abs().sum()) == 0
+    AL, Lm, eta = lc.AL.cpu().numpy(), lc.L.cpu().numpy(), lc.eta.cpu().numpy()
+    AL2, AR, C = mx.AL.cpu().numpy(), mx.AR.cpu().numpy(), mx.C.cpu().numpy()
+    assert np.array_equal(AL, AL2)
+    I = np.eye(D)
+    for k in range(count):
+        AL0, AR0, C0 = O.mixed(A[k])
+        eta0 = O.eigs(A[k])[0]
+        w = np.sort(np.abs(np.linalg.eigvals(O.transfer_matrix(A[k]))))[::-1]
+        tol = 10 * TOL / min(1.0, 1 - w[1] / w[0]) * np.linalg.cond(Lm[k])
+        assert abs(eta[k] - eta0) < TOL * abs(eta0)
+        assert np.abs(AL[k] - AL0).max() < tol
+        assert np.abs(C[k] - C0).max() < 10 * tol and np.abs(AR[k] - AR0).max() < 100 * tol
+        assert np.abs(np.einsum("sij,sik->jk", AL[k].conj(), AL[k]) - I).max() < 1e-11     # left-canonical
+        assert np.abs(np.einsum("sij,skj->ik", AR[k], AR[k].conj()) - I).max() < 1e-8     # right-canonical
+        assert np.abs(np.tril(Lm[k], -1)).max() == 0 and abs(np.trace(Lm[k].conj().T @ Lm[k]) - D) < 1e-10
+        rr, ll = C[k] @ C[k].conj().T, C[k].conj().T @ C[k]
+        EL, ER = O.transfer_matrix(AL[k]), O.transfer_matrix(AR[k])
+        assert np.abs(EL @ rr.reshape(-1) - rr.reshape(-1)).max() < 1e-10
+        assert np.abs(ER.conj().T @ ll.reshape(-1) - ll.reshape(-1)).max() < 1e-8
+
+
+def test_mixed_of_left_canonical_input_is_env_exact(env):
+    """assume_left_canonical: AL = A, C is exactly the Cholesky factor get_env_exact uses
+    (qmps/tools.py:184-186 get_env_exact_alternative == get_env_exact up to gauge)."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    for D, count in ((2, 257), (4, 31)):
+        A = t.from_numpy(tensors(D, count, 950, O)).cuda()
+        mx = B.mixed_canonical(A, assume_left_canonical=True)
+        ex = B.env_exact(A=A)
+        assert int(mx.status.abs().sum()) == 0
+        assert t.equal(mx.C, ex.C) and mx.AL.data_ptr() == A.data_ptr()
+        AR = mx.AR.cpu().numpy()
+        for k in range(0, count, 7):
+            assert O.is_right_canonical(AR[k], 1e-9)
+
+
+@pytest.mark.parametrize("D,count", [(2, 100), (4, 20), (8, 5)])
+def test_expectation_values_vs_oracle(env, D, count):
+    """iMPS.Es: gauge invariant, so the canonicalised tensor, the original tensor (general formula)
+    and the oracle must agree; for unitary-derived tensors also the energy identity
+    <O x 1> = Es(O) (qmps/ground_state.py:251-266 evaluated with H = O (x) 1)."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = _random_tensors(2, D, count, 970 + D)
+    Ad = t.from_numpy(A).cuda()
+    es_gen = B.expectation_values(Ad, _PAULIS, assume_left_canonical=False).cpu().numpy()
+    AL = B.left_canonicalise(Ad).AL
+    es_can = B.expectation_values(AL, _PAULIS).cpu().numpy()
+    for k in range(count):
+        ref = O.expectation_values(A[k], _PAULIS)
+        w = np.sort(np.abs(np.linalg.eigvals(O.transfer_matrix(A[k]))))[::-1]
+        tol = 100 * TOL / min(1.0, 1 - w[1] / w[0])
+        assert np.abs(es_gen[k] - ref).max() < tol and np.abs(es_can[k] - ref).max() < tol
+        assert np.abs(es_can[k].imag).max() < 1e-12
+    Au = t.from_numpy(tensors(D, count, 980, O)).cuda()
+    es = B.expectation_values(Au, _PAULIS).cpu().numpy()
+    for o in range(3):
+        H = np.kron(_PAULIS[o], np.eye(2))
+        e = B.energy_tensor(Au, H).cpu().numpy()
+        assert np.abs(es[:, o].real - e).max() < 1e-11
+
+
+def test_expectation_complex64_and_empty(env):
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(4, 50, 990, O)
+    e64 = B.expectation_values(t.from_numpy(A).cuda().to(t.complex64), _PAULIS).cpu().numpy()
+    e128 = B.expectation_values(t.from_numpy(A).cuda(), _PAULIS).cpu().numpy()
+    assert np.abs(e64 - e128).max() < 1e-4
+    lc = B.left_canonicalise(t.from_numpy(_random_tensors(2, 4, 20, 991)).cuda().to(t.complex64))
+    AL = lc.AL.cpu().numpy().astype(complex)
+    assert np.abs(np.einsum("nsij,nsik->njk", AL.conj(), AL) - np.eye(4)).max() < 1e-4
+    empty = t.empty((0, 2, 4, 4), dtype=t.complex128, device="cuda")
+    assert B.left_canonicalise(empty).AL.shape == (0, 2, 4, 4)
+    assert B.mixed_canonical(empty).C.shape == (0, 4, 4)
+
+
+def test_imps_compat_loop_quantities(env):
+    """The three per-step quantities of the reference's Loschmidt loop
+    (qmps/loschmidts/time_evo.py:143-145): left_canonicalise, Es(paulis), overlap."""
+    t, O = env["torch"], env["O"]
+    from qmps_b200.imps import iMPS, Map, TransferMatrix
+    rng = np.random.default_rng(5)
+    A0 = O.unitary_to_tensor(O.shallow_full_state_tensor(rng.normal(size=15)))
+    A1 = O.unitary_to_tensor(O.shallow_full_state_tensor(rng.normal(size=15)))
+    A_ = iMPS([A1]).left_canonicalise()
+    assert O.is_left_canonical(A_[0])
+    assert np.abs(A_.Es(_PAULIS) - O.expectation_values(A1, _PAULIS).real).max() < 1e-10
+    assert abs(A_.overlap(iMPS([A0])) - O.overlap(A1, A0)) < 1e-10
+    assert abs(A_.overlap(A_) - 1) < 1e-10
+    AL, AR, C = iMPS([rng.normal(size=(2, 2, 2)) + 1j * rng.normal(size=(2, 2, 2))]).mixed()
+    r, l, I = C @ C.conj().T, C.conj().T @ C, np.eye(2)
+    assert Map(AL[0], AL[0]).is_right_eigenvector(r) and Map(AL[0], AL[0]).is_left_eigenvector(I)
+    assert Map(AR[0], AR[0]).is_right_eigenvector(I) and Map(AR[0], AR[0]).is_left_eigenvector(l)
+    eta, l2, r2 = TransferMatrix(AL[0]).eigs()
+    assert abs(eta - 1) < 1e-10 and np.abs(r2 - r).max() < 1e-9 and abs(np.trace(l2 @ r2) - 1) < 1e-10

@@ -252,3 +252,53 @@ def test_emu_ansatz_and_energy(emu):
             assert np.abs(A2[0] - Aref).max() < 1e-14
             emu.emu_energy_d2(ctypes.c_int64(1), P(A2), P(H), P(e))
             assert abs(e[0] - O.energy_transfer(Aref, H)) < 1e-12
+
+
+_PAULIS = np.ascontiguousarray(np.array([[[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]], dtype=complex))
+
+
+@pytest.mark.parametrize("D", [2, 4, 8])
+def test_emu_canonical_forms_and_expectations(emu, D):
+    """canon.cuh: left_canonicalise -> mixed -> Es on random NON-canonical tensors,
+    composed exactly as the C ABI composes the device kernels (left fixed point -> gauge ->
+    environment -> gauge), against oracle/canonical.py and the properties of
+    tests/test_represent.py:23-31."""
+    N, d = 5, 2
+    rng = np.random.default_rng(40 + D)
+    A = np.ascontiguousarray(rng.normal(size=(N, d, D, D)) + 1j * rng.normal(size=(N, d, D, D)))
+    cN = ctypes.c_int64(N)
+    lvec = np.zeros((N, D, D), complex); eta = np.zeros(N, complex); st = np.zeros(N, np.int32)
+    emu.emu_fixed_point(d, D, cN, P(A), P(A), 1, P(eta), P(lvec), P(st))
+    assert st.sum() == 0
+    scale = np.ascontiguousarray(1 / np.sqrt(np.abs(eta)))
+    AL = np.zeros_like(A); Lm = np.zeros((N, D, D), complex)
+    emu.emu_gauge(d, D, cN, P(A), P(lvec), 0, P(scale), P(AL), P(Lm), P(st))
+    assert st.sum() == 0
+    r = np.zeros((N, D, D), complex); e1 = np.zeros(N, complex); C = np.zeros((N, D, D), complex)
+    emu.emu_env_generic(d, D, cN, P(AL), 1, P(e1), P(r), P(C), P(st))
+    assert st.sum() == 0
+    AR = np.zeros_like(A)
+    emu.emu_gauge(d, D, cN, P(AL), P(C), 1, None, P(AR), None, P(st))
+    es = np.zeros((N, 3), complex)
+    emu.emu_expect(d, D, cN, P(AL), P(r), None, None, 3, P(_PAULIS), P(es))
+    # the general formula on the ORIGINAL tensor: right fixed point + left vector + eta
+    rv = np.zeros((N, D, D), complex); eta_r = np.zeros(N, complex)
+    emu.emu_fixed_point(d, D, cN, P(A), P(A), 0, P(eta_r), P(rv), P(st))
+    es_gen = np.zeros((N, 3), complex)
+    emu.emu_expect(d, D, cN, P(A), P(rv), P(lvec), P(eta_r), 3, P(_PAULIS), P(es_gen))
+    I = np.eye(D)
+    for k in range(N):
+        AL0, AR0, C0 = O.mixed(A[k])
+        assert np.abs(AL[k] - AL0).max() < 1e-10 and np.abs(C[k] - C0).max() < 1e-10 and np.abs(AR[k] - AR0).max() < 1e-9
+        assert np.abs(np.triu(Lm[k], 0) - Lm[k]).max() == 0 and abs(np.trace(Lm[k].conj().T @ Lm[k]) - D) < 1e-10
+        assert O.is_left_canonical(AL[k]) and O.is_right_canonical(AR[k], 1e-9)
+        # tests/test_represent.py:23-31
+        rr, ll = C[k] @ C[k].conj().T, C[k].conj().T @ C[k]
+        EL, ER = O.transfer_matrix(AL[k]), O.transfer_matrix(AR[k])
+        assert np.abs(EL @ rr.reshape(-1) - rr.reshape(-1)).max() < 1e-10
+        assert np.abs(EL.conj().T @ I.reshape(-1) - I.reshape(-1)).max() < 1e-10
+        assert np.abs(ER @ I.reshape(-1) - I.reshape(-1)).max() < 1e-9
+        assert np.abs(ER.conj().T @ ll.reshape(-1) - ll.reshape(-1)).max() < 1e-9
+        ref = O.expectation_values(A[k], _PAULIS)
+        assert np.abs(es[k] - ref).max() < 1e-10 and np.abs(es_gen[k] - ref).max() < 1e-10
+        assert np.abs(es[k].imag).max() < 1e-12
