@@ -22,6 +22,8 @@ ncu) timeout 300 ncu --set full --clock-control none --import-source on -k regex
       python tools/profile_driver.py --what d2 > $OUT/ncu_d2.log 2>&1
      timeout 300 ncu --set full --clock-control none --import-source on -k regex:'fixed_point_kernel|env_real_kernel|env_generic_kernel|zgemm_dmma' -c 4 -f -o $OUT/prof_generic_$TAG \
       python tools/profile_driver.py --what fp4,en8,pw64 --reps 1 > $OUT/ncu_generic.log 2>&1;;
+ncutc) timeout 300 ncu --set full --clock-control none --import-source on -k regex:'cgemm_tc_kernel|gauge_kernel|expect_kernel|fp16_kernel' -c 6 -f -o $OUT/prof_tc_$TAG \
+      python tools/profile_driver.py --what tc64,tc256,fp4,canon --reps 1 > $OUT/ncu_tc.log 2>&1; tail -3 $OUT/ncu_tc.log;;
 esac
 done
 ls -la $OUT | tail -30

@@ -69,6 +69,12 @@ def main():
             Bt = torch.view_as_complex(torch.randn((N, 2, D, D, 2), dtype=torch.float32, device=dev, generator=g)) / np.sqrt(2 * D)
             for _ in range(args.reps):
                 B.tm_power(A, Bt, 2)
+    if "canon" in what:                   # gauge fixing + local expectation values
+        for D in (2, 4):
+            A = torch.view_as_complex(torch.randn((1 << 16, 2, D, D, 2), dtype=torch.float64, device=dev, generator=g))
+            for _ in range(args.reps):
+                m = B.mixed_canonical(A)
+                B.expectation_values(m.AL, np.stack([np.array([[1, 0], [0, -1]]), np.array([[0, 1], [1, 0]])]))
     torch.cuda.synchronize()
     print("profile_driver done:", what)
 
