@@ -122,6 +122,8 @@ int qmps_set_option(const char* name, int value) {
   if (!strcmp(name, "env_real")) { g_options[OPT_ENV_REAL] = value; return 0; }
   if (!strcmp(name, "tc_power")) { g_options[OPT_TC_POWER] = value; return 0; }
   if (!strcmp(name, "tc_persistent")) { g_options[OPT_TC_PERSISTENT] = value; return 0; }
+  if (!strcmp(name, "fp_group")) { g_options[OPT_FP_GROUP] = value; return 0; }
+  if (!strcmp(name, "fp_block")) { g_options[OPT_FP_BLOCK] = value; return 0; }
   return fail(QMPS_ERR_ARG, std::string("set_option: unknown option ") + name);
 }
 int qmps_debug_counters(unsigned long long* out4, int reset) {

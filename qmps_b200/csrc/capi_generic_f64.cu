@@ -65,7 +65,8 @@ int launch_fp16(FpParams p, cudaStream_t st) {
 template <int G> int launch_fp(FpParams p, cudaStream_t st) {
   const int n = p.D * p.D;
   const int h_in_smem = n <= 64;
-  const int block = G > 32 ? G : 128;
+  int block = G > 32 ? G : 128;
+  if (G <= 32 && option_get(OPT_FP_BLOCK) >= 32 && option_get(OPT_FP_BLOCK) <= 128) block = option_get(OPT_FP_BLOCK) & ~31;
   const int gpc = G > 32 ? 1 : block / G;
   const FpLayout<REAL> L = fp_layout<REAL>(p.D, h_in_smem);
   const size_t smem = L.total * gpc;
@@ -117,6 +118,8 @@ int fp16_debug_f64(unsigned long long* out, int reset) {
 }
 int fixed_point_f64(const FpParams& p, cudaStream_t st) {
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
+  if (p.D == 4 && option_get(OPT_FP_GROUP) == 8) return launch_fp<8>(p, st);
+  if (p.D == 4 && option_get(OPT_FP_GROUP) == 4) return launch_fp<4>(p, st);
   switch (group_for_n(p.D * p.D)) {
     case 4: return launch_fp<4>(p, st);
     case 16: return launch_fp<16>(p, st);
