@@ -228,6 +228,46 @@ int qmps_gauge_transform(int d, int D, int64_t N, const void* A, const void* X, 
 int qmps_expectation(int d, int D, int64_t N, const void* A, const void* r, const void* lvec,
                      const void* eta, int nops, const void* ops, void* out, int dtype, void* stream);
 
+/* ---- two-layer brick-wall iMPS family (new_tdvp/ClassicalTDVPStripped.py) --------------
+ * Unitaries are 4x4, row-major: U[(a,b),(c,d)] = U.reshape(2,2,2,2)[a,b,c,d].  (U1, U2) is the ket
+ * state, (U1_, U2_) what the reference passes as `U1_`, `U2_` -- ALREADY daggered by the caller -- unless
+ * bra_undaggered = 1: then the arrays hold the candidate unitaries V1, V2 themselves (what paramU returns,
+ * :159-180) and the daggers are formed on the device.  Every array count (NK, NB, NM, NO, NW) is N or 1
+ * (1 = shared by the whole batch). */
+
+/* RightEnvironment / LeftEnvironment .exact_environment_circuit + .exact_environment (:322-352, :394-426):
+ *     side 0 = right, 1 = left.  Optional out: mat [N][4][4] the 4x4 map; eta [N] its eigenvalue selected
+ *     by numpy's complex argmax (lexicographic on (real, imag) -- the reference's rule, not the largest
+ *     modulus); vec [N][2][2] the eigenvector in scipy.linalg.eig's (zgeev) gauge: unit 2-norm, component
+ *     of largest modulus real positive; status [N] (QMPS_ST_NO_CONVERGE). */
+int qmps_bw_environment(int side, int64_t N, int64_t NK, const void* U1, const void* U2, int64_t NB,
+                        const void* U1_, const void* U2_, int bra_undaggered, void* mat, void* eta,
+                        void* vec, int32_t* status, int dtype, void* stream);
+
+/* RightEnvironment.circuit(U1, U2, U1_, U2_, M) (:360-384): one application of the right map to
+ *     M [NM][2][2] -> out [N][2][2]. */
+int qmps_bw_env_apply(int64_t N, int64_t NK, const void* U1, const void* U2, int64_t NB, const void* U1_,
+                      const void* U2_, int bra_undaggered, int64_t NM, const void* M, void* out, int dtype,
+                      void* stream);
+
+/* OverlapCalculator.expectation_value(U1, U2, O) (:428-533): Re <psi| 1 (x) O (x) 1 |psi> with
+ *     op_qubits = 2 (O [NO][4][4], 4-qubit state) or 4 (O [NO][16][16], 6-qubit state); out [N] real. */
+int qmps_bw_expectation(int64_t N, int64_t NK, const void* U1, const void* U2, int op_qubits, int64_t NO,
+                        const void* O, void* out, int dtype, void* stream);
+
+/* ManifoldOverlap.circuit(U1, U2, U1_, U2_, Mr, Ml, W) (:228-268): <phi| Ml (x) W (x) Mr |psi> on six
+ *     qubits; Mr, Ml [NM][2][2], W [NW][16][16]; overlap [N] complex. */
+int qmps_bw_overlap(int64_t N, int64_t NK, const void* U1, const void* U2, int64_t NB, const void* U1_,
+                    const void* U2_, int bra_undaggered, int64_t NM, const void* Mr, const void* Ml, int64_t NW,
+                    const void* W, void* overlap, int dtype, void* stream);
+
+/* body of Evolve.exact_cost_function (:777-790) for candidate unitaries V1, V2 [NB][4][4] (undaggered):
+ *     Mr = exact right environment of the mixed map, overlap with (Mr, Mr^dagger) and W, cost = -|overlap|^2,
+ *     all in one launch.  cost [N] real; optional overlap [N], eta [N], Mr [N][2][2], status [N]. */
+int qmps_bw_evolve_cost(int64_t N, int64_t NK, const void* U1, const void* U2, int64_t NB, const void* V1,
+                        const void* V2, int64_t NW, const void* W, void* cost, void* overlap, void* eta, void* Mr,
+                        int32_t* status, int dtype, void* stream);
+
 /* (e)  local part of the final cost reduction: (min cost, argmin + index_offset) of a
  *     DEVICE array, written to DEVICE best_cost[1] / best_index[1]; the cross-rank
  *     step is one NCCL all-gather of 16 bytes per rank (qmps_b200/dist.py). */

@@ -53,6 +53,11 @@ SIGNATURES = {
     "qmps_mixed_canonical": ([_i, _i, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_gauge_transform": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_expectation": ([_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp], _i),
+    "qmps_bw_environment": ([_i, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_bw_env_apply": ([_i64, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp], _i),
+    "qmps_bw_expectation": ([_i64, _i64, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp], _i),
+    "qmps_bw_overlap": ([_i64, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _i64, _vp, _vp, _i, _vp], _i),
+    "qmps_bw_evolve_cost": ([_i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_argmin": ([_i64, _vp, _i64, _vp, _vp, _vp], _i),
     "qmps_loschmidt_rate": ([_i64, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp], _i),
 }

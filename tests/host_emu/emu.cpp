@@ -12,6 +12,7 @@
 #include "../../qmps_b200/csrc/d2.cuh"
 #include "../../qmps_b200/csrc/envreal.cuh"
 #include "../../qmps_b200/csrc/canon.cuh"
+#include "../../qmps_b200/csrc/brickwall.cuh"
 
 using namespace qmps;
 typedef cx<double> zc;
@@ -209,6 +210,53 @@ int emu_expect(int d, int D, int64_t N, const double* A, const double* r, const 
                            lvec ? (const zc*)lvec + p * (size_t)n : nullptr, eta ? (const zc*)eta + p : nullptr,
                            (const zc*)ops, nops, d, D, sA.data(), sR.data(), sL.data(), sP.data(), sQ.data(), sM.data(),
                            (zc*)out + p * (size_t)nops);
+  return 0;
+}
+
+// brickwall.cuh: the body of bw_kernel for one problem at a time (mode numbering of kernels_bw.cuh:
+// 0 env, 1 apply, 2 expect, 3 overlap, 4 cost).  Arrays as in include/qmps_b200.h; counts 1 broadcast.
+int emu_brickwall(int mode, int side, int bra_undaggered, int mbits, int64_t N, int64_t NK, const double* U1,
+                  const double* U2, int64_t NB, const double* B1, const double* B2, int64_t NM, const double* Mr,
+                  const double* Ml, int64_t NW, const double* Wop, double* mat, double* eta, double* vec,
+                  double* overlap, double* real_out, int32_t* status) {
+  std::vector<unsigned char> buf(bw_work_bytes<double>(1) + 64);
+  Grp g = solo();
+  const BwWork<double> W = bw_carve<double>(buf.data(), 1);
+  for (int64_t p = 0; p < N; ++p) {
+    const zc* u1 = (const zc*)U1 + (NK == 1 ? 0 : p) * 16;
+    const zc* u2 = (const zc*)U2 + (NK == 1 ? 0 : p) * 16;
+    const zc* b1 = B1 ? (const zc*)B1 + (NB == 1 ? 0 : p) * 16 : nullptr;
+    const zc* b2 = B2 ? (const zc*)B2 + (NB == 1 ? 0 : p) * 16 : nullptr;
+    const int wsz = (mode == 2 && mbits == 2) ? 16 : 256;
+    const zc* wop = Wop ? (const zc*)Wop + (NW == 1 ? 0 : p) * wsz : nullptr;
+    bw_load<double>(g, u1, u2, b1, b2, bra_undaggered, W);
+    int st = 0;
+    if (mode == 0) {
+      if (mat) { bw_env_matrix<double>(g, W, side, W.E, 5); for (int e = 0; e < 16; ++e) ((zc*)mat)[p * 16 + e] = W.E[(e >> 2) * 5 + (e & 3)]; }
+      zc lam;
+      st = bw_exact_environment<double>(g, W, side, &lam, vec != nullptr);
+      if (eta) ((zc*)eta)[p] = lam;
+      if (vec) for (int e = 0; e < 4; ++e) ((zc*)vec)[p * 4 + e] = W.x[e];
+    } else if (mode == 1) {
+      bw_env_apply<double>(g, W, (const zc*)Mr + (NM == 1 ? 0 : p) * 4, (zc*)vec + p * 4);
+    } else if (mode == 2) {
+      real_out[p] = bw_expectation<double>(g, W, wop, mbits);
+    } else {
+      if (mode == 4) {
+        zc lam;
+        st = bw_exact_environment<double>(g, W, 0, &lam, 1);
+        for (int e = 0; e < 4; ++e) { W.mr[e] = W.x[e]; W.ml[e] = conj(W.x[(e & 1) * 2 + (e >> 1)]); }
+        if (eta) ((zc*)eta)[p] = lam;
+        if (vec) for (int e = 0; e < 4; ++e) ((zc*)vec)[p * 4 + e] = W.x[e];
+      } else {
+        for (int e = 0; e < 4; ++e) { W.mr[e] = ((const zc*)Mr)[(NM == 1 ? 0 : p) * 4 + e]; W.ml[e] = ((const zc*)Ml)[(NM == 1 ? 0 : p) * 4 + e]; }
+      }
+      const zc ov = bw_overlap<double>(g, W, wop);
+      if (overlap) ((zc*)overlap)[p] = ov;
+      if (real_out) real_out[p] = -(ov.re * ov.re + ov.im * ov.im);
+    }
+    if (status) status[p] = st;
+  }
   return 0;
 }
 
