@@ -26,6 +26,9 @@ Parity pinning status (see DESIGN.md section "Oracle"):
   ``tests/test_ground_state.py:101-102``, ``D2_gse`` of
   ``scripts/noisy_optimization.py:93``, the known-answer environment of
   ``new_tdvp/testTDVPStripped.py:156-170``.
+* PINNED, brick-wall family (``oracle/brickwall.py``): every function against outputs of the
+  reference's unmodified ``new_tdvp/ClassicalTDVPStripped.py`` run under stub modules
+  (``oracle/make_golden_bw.py`` -> ``tests/golden/ref_brickwall.npz``).
 * PARITY UNPINNED: everything whose arithmetic lives in the un-vendored,
   un-pinned third-party packages ``xmps`` (``TransferMatrix.eigs``,
   ``Map.right_fixed_point``/``left_fixed_point``, ``iMPS.left_canonicalise``,
@@ -39,3 +42,4 @@ from .tensors import *      # noqa: F401,F403
 from .gates import *        # noqa: F401,F403
 from .costs import *        # noqa: F401,F403
 from .canonical import *    # noqa: F401,F403
+from .brickwall import *    # noqa: F401,F403

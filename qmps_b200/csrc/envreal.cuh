@@ -74,6 +74,104 @@ QMPS_HD void herm_row(const cx<T>* Ap, int lda, int d, int e, T* m) {
   }
 }
 
+// Same row, for a compile-time physical dimension DP: the D*DP entries A[s][i][:] of "my" left
+// index stay in registers and only A[s][k][:] is streamed from shared memory -- 88 instead of 240
+// 16-byte shared loads per row at D = 8, DP = 2 (the row build was LSU-bound:
+// profiles/ncu_er8_src_r01f.txt).  Identical arithmetic order per entry as herm_row.
+template <typename T, int D, int DP>
+QMPS_HD void herm_row_cached(const cx<T>* Ap, int lda, int e, T* m) {
+  constexpr int n = D * D;
+  int i, k, part;
+  herm_index<D>(e, &i, &k, &part);
+  const cx<T>* Ai = Ap + i * lda;
+  const cx<T>* Ak = Ap + k * lda;
+  const int sstride = D * lda;
+  cx<T> ai[DP][D];
+#pragma unroll
+  for (int s = 0; s < DP; ++s)
+#pragma unroll
+    for (int j = 0; j < D; ++j) ai[s][j] = Ai[s * sstride + j];
+#pragma unroll
+  for (int l = 0; l < D; ++l) {
+    cx<T> bl[DP];
+#pragma unroll
+    for (int s = 0; s < DP; ++s) bl[s] = Ak[s * sstride + l];
+    {
+      cx<T> g = mk<T>(0, 0);
+#pragma unroll
+      for (int s = 0; s < DP; ++s) cmad_c(g, ai[s][l], bl[s]);
+      m[l] = (part ? g.im : g.re) - (e == l ? T(1) : T(0));
+    }
+#pragma unroll
+    for (int j = 0; j < l; ++j) {
+      const int u = D + 2 * (j * D - (j * (j + 1)) / 2 + (l - j - 1));
+      cx<T> g1 = mk<T>(0, 0), g2 = mk<T>(0, 0);
+#pragma unroll
+      for (int s = 0; s < DP; ++s) {
+        const cx<T> akj = Ak[s * sstride + j];
+        cmad_c(g1, ai[s][j], bl[s]);        // G(j,l)
+        cmad_c(g2, ai[s][l], akj);          // G(l,j)
+      }
+      const T cx_re = g1.re + g2.re, cx_im = g1.im + g2.im;
+      const T cy_re = -(g1.im - g2.im), cy_im = g1.re - g2.re;
+      m[u] = (part ? cx_im : cx_re) - (e == u ? T(1) : T(0));
+      m[u + 1] = (part ? cy_im : cy_re) - (e == u + 1 ? T(1) : T(0));
+    }
+  }
+  m[n] = T(0);
+  if (e == 0) {
+#pragma unroll
+    for (int uu = 0; uu < n; ++uu) m[uu] = uu < D ? T(1) : T(0);
+    m[n] = T(1);
+  }
+}
+
+// Middle ground for the register-capped complex128 D = 8 kernel: only the l-side operands
+// (A[s][i][l], A[s][k][l]) are hoisted out of the pair loop -- 144 instead of 240 shared loads per
+// row for 8 extra live doubles.  Same arithmetic order per entry as herm_row.
+template <typename T, int D, int DP>
+QMPS_HD void herm_row_lhoist(const cx<T>* Ap, int lda, int e, T* m) {
+  constexpr int n = D * D;
+  int i, k, part;
+  herm_index<D>(e, &i, &k, &part);
+  const cx<T>* Ai = Ap + i * lda;
+  const cx<T>* Ak = Ap + k * lda;
+  const int sstride = D * lda;
+#pragma unroll
+  for (int l = 0; l < D; ++l) {
+    cx<T> ail[DP], akl[DP];
+#pragma unroll
+    for (int s = 0; s < DP; ++s) { ail[s] = Ai[s * sstride + l]; akl[s] = Ak[s * sstride + l]; }
+    {
+      cx<T> g = mk<T>(0, 0);
+#pragma unroll
+      for (int s = 0; s < DP; ++s) cmad_c(g, ail[s], akl[s]);
+      m[l] = (part ? g.im : g.re) - (e == l ? T(1) : T(0));
+    }
+#pragma unroll
+    for (int j = 0; j < l; ++j) {
+      const int u = D + 2 * (j * D - (j * (j + 1)) / 2 + (l - j - 1));
+      cx<T> g1 = mk<T>(0, 0), g2 = mk<T>(0, 0);
+#pragma unroll
+      for (int s = 0; s < DP; ++s) {
+        const cx<T> aij = Ai[s * sstride + j], akj = Ak[s * sstride + j];
+        cmad_c(g1, aij, akl[s]);            // G(j,l)
+        cmad_c(g2, ail[s], akj);            // G(l,j)
+      }
+      const T cx_re = g1.re + g2.re, cx_im = g1.im + g2.im;
+      const T cy_re = -(g1.im - g2.im), cy_im = g1.re - g2.re;
+      m[u] = (part ? cx_im : cx_re) - (e == u ? T(1) : T(0));
+      m[u + 1] = (part ? cy_im : cy_re) - (e == u + 1 ? T(1) : T(0));
+    }
+  }
+  m[n] = T(0);
+  if (e == 0) {
+#pragma unroll
+    for (int uu = 0; uu < n; ++uu) m[uu] = uu < D ? T(1) : T(0);
+    m[n] = T(1);
+  }
+}
+
 // solution vector x[n] -> Hermitian r (row-major D x D, unpadded); one entry pair per call
 template <typename T, int D> QMPS_HD void herm_scatter(const T* x, int e, cx<T>* r) {
   int i, k, part;

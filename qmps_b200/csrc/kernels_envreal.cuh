@@ -28,7 +28,7 @@ QMPS_HD ErLayout<T, D> er_layout(int d, int nops, int want_tmp) {
   L.A = b.take(sizeof(cx<T>) * (size_t)d * n);                  // unpadded (ansatz state / energy)
   L.Ap = b.take(sizeof(cx<T>) * (size_t)d * D * (D + 1));       // padded rows for the row build
   L.rowbuf = b.take(sizeof(T) * 2 * NW * (n + 2));
-  L.cand = b.take(sizeof(T) * 2 * NW * 2);
+  L.cand = b.take(sizeof(T) * 2 * NW * 4);
   L.x = b.take(sizeof(T) * n);
   L.r = b.take(sizeof(cx<T>) * n);
   L.C = b.take(sizeof(cx<T>) * n);
@@ -46,8 +46,11 @@ template <> struct tiny_of<double> { static __device__ __forceinline__ double v(
 template <> struct tiny_of<float> { static __device__ __forceinline__ float v() { return 1e-5f; } };
 
 // MODE 0: eta, r, C, status.  MODE 1: energy (+ status).
-template <typename T, int D, int MODE>
-__global__ void __launch_bounds__(D == 8 ? 64 : 128, D == 8 ? 5 : 4)
+// WIDE (D = 8 only): 1 = 255 registers / 4 CTAs per SM with the register-cached row builder, instead
+// of 168 registers / 6 CTAs per SM (3 warps on one SM sub-partition) with the streaming one (0) or the
+// l-hoisted one (2).
+template <typename T, int D, int MODE, int WIDE>
+__global__ void __launch_bounds__(D == 8 ? 64 : 128, (D == 8 && WIDE != 1) ? 5 : 4)
 env_real_kernel(EnvParams p) {
   constexpr int n = D * D, NT = n, NW = (NT + 31) / 32;
   constexpr int G = NT;                                     // lanes per problem
@@ -106,7 +109,9 @@ env_real_kernel(EnvParams p) {
     g.sync();
     // ---- 2. my row of the real system, in registers
     T m[n + 1];
-    herm_row<T, D>(Ap, D + 1, d, e, m);
+    if (d == 2 && (WIDE == 1 || D < 8)) herm_row_cached<T, D, 2>(Ap, D + 1, e, m);
+    else if (d == 2 && WIDE == 2) herm_row_lhoist<T, D, 2>(Ap, D + 1, e, m);
+    else herm_row<T, D>(Ap, D + 1, d, e, m);
     // ---- 3. Gauss-Jordan, implicit partial pivoting
     bool done = false;
     int bad = 0;
@@ -118,13 +123,16 @@ env_real_kernel(EnvParams p) {
       // the top 26 bits of |m[k]| as a float (monotonic in the magnitude) | (63 - row).  Partial
       // pivoting only needs a pivot within rounding of the largest, not the exact maximum.
       const T cand_exact = done ? T(-1) : fabs(m[k]);
+      // 1/m[k] of MY row, started before the arg-max so the division latency hides behind the
+      // reduction, the publish and the barrier; only the winner's value is used
+      const T myinv = T(1) / m[k];
       unsigned key = done ? 0u : ((__float_as_uint((float)cand_exact) & ~63u) | (unsigned)(63 - e));
       if (!done && key < 64u) key = 64u | (unsigned)(63 - e);       // zero column entry: still eligible
       const unsigned best = __reduce_max_sync(smask, key);
       int who = 63 - (int)(best & 63u);
       T cand = __uint_as_float(best & ~63u);
       T* buf = rowbuf + ((k & 1) * NW + wig) * ROWLD;
-      T* cb = candbuf + ((k & 1) * NW + wig) * 2;
+      T* cb = candbuf + ((k & 1) * NW + wig) * 4;
       if (e == who) {                                         // local winner publishes its row
         {
           int j = k;
@@ -135,23 +143,25 @@ env_real_kernel(EnvParams p) {
         }
         cb[0] = cand;
         cb[1] = T(who);
+        cb[2] = myinv;
       }
       if (NW > 1 && best == 0u && (e & 31) == 0) cb[0] = T(-1);   // this warp has no unused row left
       g.sync();
       int gwho = who;
       const T* prow = buf;
       if (NW > 1) {                                           // best of the warps' candidates
-        const T* c0 = candbuf + ((k & 1) * NW) * 2;
+        const T* c0 = candbuf + ((k & 1) * NW) * 4;
         T bc = c0[0]; int bw = 0;
 #pragma unroll
-        for (int w = 1; w < NW; ++w) { const T cw = c0[2 * w]; if (cw > bc) { bc = cw; bw = w; } }
-        gwho = (int)c0[2 * bw + 1];
+        for (int w = 1; w < NW; ++w) { const T cw = c0[4 * w]; if (cw > bc) { bc = cw; bw = w; } }
+        gwho = (int)c0[4 * bw + 1];
+        cb = candbuf + ((k & 1) * NW + bw) * 4;
         prow = rowbuf + ((k & 1) * NW + bw) * ROWLD;
         cand = bc;
       }
       if (!(cand > tiny_of<T>::v())) bad = 1;
       const T pv = prow[k];
-      const T inv = T(1) / pv;
+      const T inv = cb[2];
       T f = m[k] * inv;
       if (e == gwho) { done = true; mypiv = pv; mycol = k; f = T(0); }
       {

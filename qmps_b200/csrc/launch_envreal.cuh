@@ -6,7 +6,7 @@
 
 namespace qmps_host {
 
-template <typename REAL, int D, int MODE>
+template <typename REAL, int D, int MODE, int WIDE>
 int launch_env_real(qmps::EnvParams p, cudaStream_t st) {
   using namespace qmps;
   constexpr int n = D * D;
@@ -14,7 +14,7 @@ int launch_env_real(qmps::EnvParams p, cudaStream_t st) {
   const int gpc = block / n;
   const ErLayout<REAL, D> L = er_layout<REAL, D>(p.d, p.nops, MODE == 1);
   const size_t smem = L.total * gpc;
-  auto kern = env_real_kernel<REAL, D, MODE>;
+  auto kern = env_real_kernel<REAL, D, MODE, WIDE>;
   if (int rc = allow_smem(kern, smem)) return rc;
   const int S = (MODE == 1 && p.nshift > 0) ? p.nshift : 1;
   const int64_t total = p.N * S;
@@ -33,7 +33,13 @@ inline bool env_real_applies(const qmps::EnvParams& p) {
 
 template <typename REAL, int MODE>
 int dispatch_env_real(const qmps::EnvParams& p, cudaStream_t st) {
-  return p.D == 4 ? launch_env_real<REAL, 4, MODE>(p, st) : launch_env_real<REAL, 8, MODE>(p, st);
+  if (p.D == 4) return launch_env_real<REAL, 4, MODE, 0>(p, st);
+  // er_wide: -1 = measured best per precision (profiles/sweep_er_r01*.jsonl), 0 / 1 / 2 force a variant
+  int v = option_get(OPT_ER_WIDE);
+  if (v < 0) v = sizeof(REAL) == 4 ? 1 : 0;
+  if (v == 1) return launch_env_real<REAL, 8, MODE, 1>(p, st);
+  if (v == 2) return launch_env_real<REAL, 8, MODE, 2>(p, st);
+  return launch_env_real<REAL, 8, MODE, 0>(p, st);
 }
 
 }  // namespace qmps_host

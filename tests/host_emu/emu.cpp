@@ -26,7 +26,11 @@ template <int D> static int env_real_one(const zc* A, int d, zc* r) {
   std::vector<zc> Ap((size_t)d * D * (D + 1));
   for (int q = 0; q < d * n; ++q) Ap[(q / D) * (D + 1) + q % D] = A[q];
   std::vector<double> M((size_t)n * (n + 1));
-  for (int e = 0; e < n; ++e) herm_row<double, D>(Ap.data(), D + 1, d, e, &M[(size_t)e * (n + 1)]);
+  for (int e = 0; e < n; ++e) {      // same dispatch as env_real_kernel
+    if (d == 2 && (e & 1)) herm_row_cached<double, D, 2>(Ap.data(), D + 1, e, &M[(size_t)e * (n + 1)]);
+    else if (d == 2) herm_row_lhoist<double, D, 2>(Ap.data(), D + 1, e, &M[(size_t)e * (n + 1)]);
+    else herm_row<double, D>(Ap.data(), D + 1, d, e, &M[(size_t)e * (n + 1)]);
+  }
   std::vector<int> done(n, 0), col_of(n, 0);
   std::vector<double> piv(n, 1.0), x(n);
   int bad = 0;

@@ -220,10 +220,14 @@ def test_gpu_brickwall_batch_vs_oracle_and_broadcast(built):
     # complex64 mode: 1e-5
     c32 = BW.bw_evolve_cost(torch.from_numpy(U1).to(torch.complex64).cuda(), U2, V1, V2, W).cpu().numpy()
     assert c32.dtype == np.float32 and np.abs(c32 - cost).max() < 2e-5
-    # W = 1 and candidate = state: cost -1 (testTDVPStripped.py:180-191)
+    # W = 1 and candidate = state: the exact environment is 1/sqrt(2) (unit 2-norm, testTDVPStripped.py:169),
+    # so overlap = <psi| Mr^dagger (x) 1 (x) Mr |psi> = 1/2 and the cost is -1/4 (the reference's own
+    # :180-191 check passes M = eye(2) and gets -1: covered below through ManifoldOverlap.circuit)
     Us1, Us2 = _haar(4, 64, 21), _haar(4, 64, 22)
     c1 = BW.bw_evolve_cost(Us1, Us2, Us1, Us2, np.eye(16)).cpu().numpy()
-    assert np.abs(c1 + 1).max() < 1e-10
+    assert np.abs(c1 + 0.25).max() < 1e-10
+    ov1 = BW.bw_overlap(Us1, Us2, dag(Us1), dag(Us2), np.eye(2), np.eye(2), np.eye(16)).cpu().numpy()
+    assert np.abs(-np.abs(ov1) ** 2 + 1).max() < 1e-10
     # expectation values: Hermitian operator -> value inside the spectrum; identity -> 1
     e1 = BW.bw_expectation(Us1, Us2, np.eye(16)).cpu().numpy()
     assert np.abs(e1 - 1).max() < 1e-12
@@ -256,4 +260,4 @@ def test_gpu_brickwall_reference_classes_known_answers(built):
     rs = np.random.RandomState(3)
     U1, U2 = unitary_group.rvs(4, random_state=rs), unitary_group.rvs(4, random_state=rs)
     ev = BW.Evolve(W=np.eye(16), U1=U1, U2=U2)
-    assert np.isclose(ev.exact_cost_function_unitaries(U1, U2), -1)
+    assert np.isclose(ev.exact_cost_function_unitaries(U1, U2), -0.25)

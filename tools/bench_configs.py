@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Device-time throughput of BASELINE.json configs 2..5 at their full sizes (one GPU).
+"""Device-time throughput of BASELINE.json configs 2..5 at their full sizes (one GPU); 6 = brick-wall cost.
 
 Not the driver's bench (that is ../bench.py, config 2): this is the measurement tool
 behind DESIGN.md's per-kernel roofline table.  CUDA events on the launching stream,
@@ -93,6 +93,23 @@ def main():
                 apps = N * (K + 1)
                 out.append({"cfg": 5, "dtype": tag, "what": f"power method D={D}", "N": N, "K": K, "ms": med, "ms_best": best,
                             "applications_per_s": apps / med * 1e3, "algo_tflops": apps * 32.0 * D ** 3 / med * 1e3 / 1e12})
+        if 6 in cfgs:                      # brick-wall TDVP step cost, one ket state, N candidates
+            from qmps_b200 import brickwall as BW
+            N = int((1 << 20) * args.scale)
+            g = torch.Generator(device=dev).manual_seed(6)
+
+            def haar(n):
+                Z = torch.randn((n, 4, 4), dtype=torch.float64, device=dev, generator=g) + 1j * torch.randn((n, 4, 4), dtype=torch.float64, device=dev, generator=g)
+                return torch.linalg.qr(Z)[0].to(cdt).contiguous()
+            U1, U2, V1, V2 = haar(1), haar(1), haar(N), haar(N)
+            h = np.random.default_rng(6).normal(size=(16, 16))
+            W = torch.from_numpy(expm(-0.1j * (h + h.T))).to(dev).to(cdt)
+            med, best = timed(torch, lambda: BW.bw_evolve_cost(U1, U2, V1, V2, W), args.reps, 2)
+            # algorithmic work per candidate: W application 64 x 16 complex MACs + 4 gate layers of 64 x 4 + the
+            # 4x4 eigenproblem (~2e3) ~= 1.7e4 real flops; traffic 2 x 16 complex in, one real out
+            out.append({"cfg": 6, "dtype": tag, "what": "brick-wall Evolve.exact_cost_function (4x4 env eig + 6-qubit overlap)", "N": N,
+                        "ms": med, "ms_best": best, "costs_per_s": N / med * 1e3,
+                        "algo_gbs": N * (2 * 16 * (16 if cdt == torch.complex128 else 8) + (8 if cdt == torch.complex128 else 4)) / med * 1e3 / 1e9})
     for o in out:
         print(json.dumps(o))
 
