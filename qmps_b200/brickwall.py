@@ -31,6 +31,8 @@ def _mats(x, n, dtype, device=None):
 
 
 def _batch(*counts):
+    if 0 in counts:                      # an empty per-problem array: empty batch
+        return 0
     N = max(counts)
     for c in counts:
         if c not in (1, N):

@@ -123,9 +123,6 @@ env_real_kernel(EnvParams p) {
       // the top 26 bits of |m[k]| as a float (monotonic in the magnitude) | (63 - row).  Partial
       // pivoting only needs a pivot within rounding of the largest, not the exact maximum.
       const T cand_exact = done ? T(-1) : fabs(m[k]);
-      // 1/m[k] of MY row, started before the arg-max so the division latency hides behind the
-      // reduction, the publish and the barrier; only the winner's value is used
-      const T myinv = T(1) / m[k];
       unsigned key = done ? 0u : ((__float_as_uint((float)cand_exact) & ~63u) | (unsigned)(63 - e));
       if (!done && key < 64u) key = 64u | (unsigned)(63 - e);       // zero column entry: still eligible
       const unsigned best = __reduce_max_sync(smask, key);
@@ -143,7 +140,6 @@ env_real_kernel(EnvParams p) {
         }
         cb[0] = cand;
         cb[1] = T(who);
-        cb[2] = myinv;
       }
       if (NW > 1 && best == 0u && (e & 31) == 0) cb[0] = T(-1);   // this warp has no unused row left
       g.sync();
@@ -155,13 +151,12 @@ env_real_kernel(EnvParams p) {
 #pragma unroll
         for (int w = 1; w < NW; ++w) { const T cw = c0[4 * w]; if (cw > bc) { bc = cw; bw = w; } }
         gwho = (int)c0[4 * bw + 1];
-        cb = candbuf + ((k & 1) * NW + bw) * 4;
         prow = rowbuf + ((k & 1) * NW + bw) * ROWLD;
         cand = bc;
       }
       if (!(cand > tiny_of<T>::v())) bad = 1;
       const T pv = prow[k];
-      const T inv = cb[2];
+      const T inv = T(1) / pv;
       T f = m[k] * inv;
       if (e == gwho) { done = true; mypiv = pv; mycol = k; f = T(0); }
       {

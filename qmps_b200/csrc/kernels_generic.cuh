@@ -173,15 +173,19 @@ template <typename T> QMPS_HD FpLayout<T> fp_layout(int D, int h_in_smem) {
   FpLayout<T> L;
   Bump b;
   const int n = D * D;
+  // Scratch with disjoint lifetimes shares storage (5.2 KB instead of 5.9 KB per 16 x 16 complex128
+  // problem: 5 instead of 4 CTAs per SM): vv is live in hessenberg only, rc / rs / rn in the QR sweeps,
+  // x / step / done in the inverse iteration that follows, and the leading eigenvalue is copied out
+  // of w before that.
   L.H = b.take(h_in_smem ? sizeof(cx<T>) * (size_t)n * (n + 1) : 0);
   L.w = b.take(sizeof(cx<T>) * n);
-  L.vv = b.take(sizeof(cx<T>) * n);
   L.rc = b.take(sizeof(cx<T>) * n);
   L.rs = b.take(sizeof(cx<T>) * n);
   L.rn = b.take(sizeof(T) * n);
-  L.x = b.take(sizeof(cx<T>) * n);
-  L.step = b.take(sizeof(int) * n);
-  L.done = b.take(sizeof(int) * n);
+  L.vv = L.rs;
+  L.x = L.rc;
+  L.step = L.rn;      // n ints <= n reals
+  L.done = L.w;       // n ints <= n complex
   L.total = b.off;
   return L;
 }

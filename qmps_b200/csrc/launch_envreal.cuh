@@ -36,7 +36,7 @@ int dispatch_env_real(const qmps::EnvParams& p, cudaStream_t st) {
   if (p.D == 4) return launch_env_real<REAL, 4, MODE, 0>(p, st);
   // er_wide: -1 = measured best per precision (profiles/sweep_er_r01*.jsonl), 0 / 1 / 2 force a variant
   int v = option_get(OPT_ER_WIDE);
-  if (v < 0) v = sizeof(REAL) == 4 ? 1 : 0;
+  if (v < 0) v = sizeof(REAL) == 4 ? 2 : 0;
   if (v == 1) return launch_env_real<REAL, 8, MODE, 1>(p, st);
   if (v == 2) return launch_env_real<REAL, 8, MODE, 2>(p, st);
   return launch_env_real<REAL, 8, MODE, 0>(p, st);

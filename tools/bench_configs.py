@@ -96,11 +96,11 @@ def main():
         if 6 in cfgs:                      # brick-wall TDVP step cost, one ket state, N candidates
             from qmps_b200 import brickwall as BW
             N = int((1 << 20) * args.scale)
-            g = torch.Generator(device=dev).manual_seed(6)
+            rng6 = np.random.default_rng(6)
 
-            def haar(n):
-                Z = torch.randn((n, 4, 4), dtype=torch.float64, device=dev, generator=g) + 1j * torch.randn((n, 4, 4), dtype=torch.float64, device=dev, generator=g)
-                return torch.linalg.qr(Z)[0].to(cdt).contiguous()
+            def haar(n):                   # numpy QR on the host (set-up only)
+                Z = rng6.normal(size=(n, 4, 4)) + 1j * rng6.normal(size=(n, 4, 4))
+                return torch.from_numpy(np.ascontiguousarray(np.linalg.qr(Z)[0])).to(dev).to(cdt).contiguous()
             U1, U2, V1, V2 = haar(1), haar(1), haar(N), haar(N)
             h = np.random.default_rng(6).normal(size=(16, 16))
             W = torch.from_numpy(expm(-0.1j * (h + h.T))).to(dev).to(cdt)

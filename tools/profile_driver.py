@@ -75,6 +75,18 @@ def main():
             for _ in range(args.reps):
                 m = B.mixed_canonical(A)
                 B.expectation_values(m.AL, np.stack([np.array([[1, 0], [0, -1]]), np.array([[0, 1], [1, 0]])]))
+    if "bw" in what:                      # brick-wall TDVP step cost
+        from qmps_b200 import brickwall as BW
+
+        rng = np.random.default_rng(6)
+
+        def haar(n, m=4):                  # numpy QR on the host: torch's batched QR launches per matrix
+            Z = rng.normal(size=(n, m, m)) + 1j * rng.normal(size=(n, m, m))
+            return torch.from_numpy(np.ascontiguousarray(np.linalg.qr(Z)[0])).to(dev)
+        U1, U2, V1, V2 = haar(1), haar(1), haar(1 << 18), haar(1 << 18)
+        W = haar(1, 16)[0].contiguous()
+        for _ in range(args.reps):
+            BW.bw_evolve_cost(U1, U2, V1, V2, W)
     torch.cuda.synchronize()
     print("profile_driver done:", what)
 
