@@ -316,11 +316,25 @@ int qmps_rotosolve_fit(int64_t N, int nshift, const double* cost, double* theta_
 int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh,
                   int dtype, void* stream) {
   if (d < 1 || D < 1 || N < 0 || K < 0 || (N && (!A || !B || !r_io))) return fail(QMPS_ERR_ARG, "tm_power: bad arguments");
-  if (N * d > 65535) return fail(QMPS_ERR_UNSUPPORTED, "tm_power: N*d > 65535 (split the batch)");
-  if (dtype == QMPS_C128) return tm_power_f64(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
-  if (dtype == QMPS_C64 && tm_power_tc_applies(d, D, N)) return tm_power_tc(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
-  if (dtype == QMPS_C64) return tm_power_impl<float>(d, D, N, A, B, r_io, K, rayleigh, (cudaStream_t)stream);
-  return fail(QMPS_ERR_ARG, "tm_power: bad dtype");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "tm_power: bad dtype");
+  // problems are independent: batches beyond the grid z-limit (N * d <= 65535) run as consecutive
+  // chunks on the same stream
+  const int64_t chunk = 65535 / d;
+  if (chunk < 1) return fail(QMPS_ERR_UNSUPPORTED, "tm_power: d > 65535");
+  const size_t csz = dtype == QMPS_C128 ? 16 : 8, DD = (size_t)D * D;
+  for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+    const int64_t n = (N - n0 < chunk) ? N - n0 : chunk;
+    const char* a = (const char*)A + csz * (size_t)n0 * d * DD;
+    const char* b = (const char*)B + csz * (size_t)n0 * d * DD;
+    char* r = (char*)r_io + csz * (size_t)n0 * DD;
+    void* ray = rayleigh ? (void*)((char*)rayleigh + csz * (size_t)n0) : nullptr;
+    int rc;
+    if (dtype == QMPS_C128) rc = tm_power_f64(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
+    else if (tm_power_tc_applies(d, D, n)) rc = tm_power_tc(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
+    else rc = tm_power_impl<float>(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C,

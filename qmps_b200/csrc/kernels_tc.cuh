@@ -46,7 +46,7 @@ constexpr int KS = 32;                         // K elements per slab (= one 128
 constexpr int PLANE_BYTES = 128 * 128;         // 128 plane rows x 128 B
 constexpr int SLAB_BYTES = 2 * PLANE_BYTES;    // hi + lo
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;    // X slab + Y slab
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;                        // 3 x 64 KB in flight per CTA (D = 64 is bound by image traffic)
 constexpr int XCH_BYTES = 128 * 64 * 4;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;

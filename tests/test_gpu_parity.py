@@ -475,6 +475,22 @@ def test_tm_power_same_tensor_converges_to_environment(env):
     assert (ray - 1).abs().max().item() < 1e-9
 
 
+def test_tm_power_batch_beyond_grid_limit(env):
+    """N * d > 65535 (the grid z-limit of the GEMM launches): consecutive chunks on one stream give the
+    same result per problem as the small batch."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    base = t.from_numpy(tensors(4, 5, 91, O)).cuda()
+    N = 32768 + 7
+    idx = t.arange(N, device="cuda") % 5
+    A, Bt = base[idx].contiguous(), base[(idx + 1) % 5].contiguous()
+    r, ray = B.tm_power(A, Bt, K=6)
+    r5, ray5 = B.tm_power(base, base[(t.arange(5, device="cuda") + 1) % 5].contiguous(), K=6)
+    assert (r - r5[idx]).abs().max().item() == 0.0 and (ray - ray5[idx]).abs().max().item() == 0.0
+    for dt in (t.complex64,):
+        r32, _ = B.tm_power(A.to(dt), Bt.to(dt), K=6)
+        assert (r32.to(t.complex128) - r).abs().max().item() < 1e-5
+
+
 def test_tm_power_complex64(env):
     t, B, O = env["torch"], env["B"], env["O"]
     A, Bt = tensors(64, 2, 464, O), tensors(64, 2, 564, O)
