@@ -3,6 +3,7 @@
 #include "api_common.cuh"
 #include "launch_envreal.cuh"
 #include "kernels_fp16.cuh"
+#include "kernels_fpd2.cuh"
 
 using namespace qmps;
 namespace qmps_host {
@@ -62,6 +63,17 @@ int launch_fp16(FpParams p, cudaStream_t st) {
   return 0;
 }
 
+// D = 2 eigenvalue-only path (kernels_fpd2.cuh): one thread per problem, registers only
+int launch_fp_d2(FpParams p, cudaStream_t st) {
+  auto kern = fp_d2_kernel<REAL>;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, 128, 0, (p.N + 127) / 128, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, 128, 0, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 template <int G> int launch_fp(FpParams p, cudaStream_t st) {
   const int n = p.D * p.D;
   const int h_in_smem = n <= 64;
@@ -108,6 +120,7 @@ int env_generic_f32(const EnvParams& p, int mode, cudaStream_t st) {
   return mode == 0 ? dispatch_env<0>(p, st) : dispatch_env<1>(p, st);
 }
 int fixed_point_f32(const FpParams& p, cudaStream_t st) {
+  if (p.D == 2 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
   // complex64, n = 16: 8 lanes per problem measured 24 % faster than 16 (profiles/sweep_fp_r01e.jsonl)
   if (p.D == 4 && (option_get(OPT_FP_GROUP) == 8 || option_get(OPT_FP_GROUP) == 0)) return launch_fp<8>(p, st);

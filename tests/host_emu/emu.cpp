@@ -13,6 +13,7 @@
 #include "../../qmps_b200/csrc/envreal.cuh"
 #include "../../qmps_b200/csrc/canon.cuh"
 #include "../../qmps_b200/csrc/brickwall.cuh"
+#include "../../qmps_b200/csrc/fp_d2.cuh"
 
 using namespace qmps;
 typedef cx<double> zc;
@@ -260,6 +261,16 @@ int emu_brickwall(int mode, int side, int bra_undaggered, int mbits, int64_t N, 
       if (real_out) real_out[p] = -(ov.re * ov.re + ov.im * ov.im);
     }
     if (status) status[p] = st;
+  }
+  return 0;
+}
+
+// fp_d2.cuh: register-resident leading eigenvalue of the D = 2 mixed map (the thread body of fp_d2_kernel)
+int emu_fp_d2(int d, int64_t N, const double* A, const double* B, int left, double* eta, int32_t* status) {
+  for (int64_t p = 0; p < N; ++p) {
+    zc lam;
+    status[p] = fpd2_leading<double>((const zc*)A + p * (size_t)d * 4, (const zc*)B + p * (size_t)d * 4, d, left, &lam);
+    eta[2 * p] = lam.re; eta[2 * p + 1] = lam.im;
   }
   return 0;
 }

@@ -208,6 +208,50 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
     assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5      # complex64 mode
 
 
+@pytest.mark.parametrize("left", [False, True])
+@pytest.mark.parametrize("d", [2, 4])
+def test_fixed_point_d2_register_kernel(env, left, d):
+    """The thread-per-problem D = 2 kernel (kernels_fpd2.cuh, eigenvalue only; the default when no
+    eigenvector is requested) against the oracle's dense eig and against the generic shared-memory
+    kernel on the same inputs; d = 4 is the merged two-site map of the Loschmidt cost.  Includes
+    identical pairs (eta = 1), near-identical pairs, the outer-product mode and an odd batch."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    count = 333
+    A, Bt = tensors(2, count, 2300 + d, O), tensors(2, count, 2900 + d, O)
+    Bt[:10] = A[:10]
+    Bt[10:20] = A[10:20] + 1e-4 * np.random.default_rng(1).normal(size=(10, 2, 2, 2))
+    if d == 4:
+        A = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", A, A).reshape(count, 4, 2, 2))
+        Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt).reshape(count, 4, 2, 2))
+    Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
+    lib = L.load()
+    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+    f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
+    outer = B.fixed_point(Ad[:7], Bd[:9], pair="outer", left=left, want_vec=False)
+    lib.qmps_set_option(b"fp_d2", 0)
+    try:
+        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+        t.cuda.synchronize()
+    finally:
+        lib.qmps_set_option(b"fp_d2", 1)
+    assert int(fast.status.abs().sum()) == 0
+    assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
+    assert (fast.cost - slow.cost).abs().max().item() < TOL and (fast.echo - slow.echo).abs().max().item() < TOL * 10
+    assert np.abs(np.abs(fast.eta[:10].cpu().numpy()) - 1).max() < 1e-12
+    for k in range(0, count, 3):
+        x0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])[0]
+        assert abs(abs(fast.eta[k].item()) - abs(x0)) < TOL
+        assert abs(fast.fid[k].item() - abs(x0) ** 2) < TOL
+        w = np.linalg.eigvals(O.transfer_matrix(A[k], Bt[k]))
+        lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
+        assert np.abs(w - lam).min() < 1e-11
+    for i in range(7):
+        for j in range(9):
+            x0 = (O.left_fixed_point if left else O.right_fixed_point)(A[i], Bt[j])[0]
+            assert abs(abs(outer.eta[i, j].item()) - abs(x0)) < TOL
+    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5      # complex64 mode
+
+
 def test_fixed_point_d4_degenerate_inputs(env):
     """Edge cases of the QR kernel: identical tensors (eta = 1 exactly known), a product state
     (rank-one map: 15 zero eigenvalues) and the zero tensor."""

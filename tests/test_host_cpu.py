@@ -227,6 +227,33 @@ def test_emu_env_real_form(emu, D):
             assert np.abs(r[k] - r0).max() < 1e-12
 
 
+@pytest.mark.parametrize("left", [0, 1])
+def test_emu_fp_d2_register_eigenvalue_path(emu, left):
+    """fp_d2.cuh: Hessenberg + QR of the 4 x 4 mixed map in registers (thread body of fp_d2_kernel)
+    against numpy's eig on the oracle's transfer matrix: single-site (d = 2) and merged two-site
+    (d = 4) tensors, near-identical pairs (eta close to 1) and exactly equal ones."""
+    N = 40
+    rs = np.random.RandomState(321)
+    for d in (2, 4):
+        A = np.stack([O.unitary_to_tensor(unitary_group.rvs(4, random_state=rs)) for _ in range(N)])
+        B = np.stack([O.unitary_to_tensor(unitary_group.rvs(4, random_state=rs)) for _ in range(N)])
+        B[:6] = A[:6]
+        B[6:12] = A[6:12] + 1e-3 * (rs.randn(6, 2, 2, 2) + 1j * rs.randn(6, 2, 2, 2))
+        if d == 4:
+            A = np.stack([O.merge(a, a) for a in A])
+            B = np.stack([O.merge(b, b) for b in B])
+        A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
+        eta = np.zeros(N, complex); st = np.zeros(N, np.int32)
+        assert emu.emu_fp_d2(d, ctypes.c_int64(N), P(A), P(B), left, P(eta), P(st)) == 0
+        assert st.sum() == 0
+        for k in range(N):
+            E = O.transfer_matrix(A[k], B[k])
+            w = np.linalg.eigvals(E.conj().T if left else E)
+            w0 = w[np.argmax(np.abs(w))]
+            assert abs(abs(eta[k]) - abs(w0)) < 1e-12
+            assert np.abs(w - eta[k]).min() < 1e-11          # it IS an eigenvalue of the map
+
+
 def test_emu_ansatz_and_energy(emu):
     from qmps_b200 import represent as R
     rng = np.random.default_rng(3)

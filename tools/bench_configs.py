@@ -110,6 +110,21 @@ def main():
             out.append({"cfg": 6, "dtype": tag, "what": "brick-wall Evolve.exact_cost_function (4x4 env eig + 6-qubit overlap)", "N": N,
                         "ms": med, "ms_best": best, "costs_per_s": N / med * 1e3,
                         "algo_gbs": N * (2 * 16 * (16 if cdt == torch.complex128 else 8) + (8 if cdt == torch.complex128 else 4)) / med * 1e3 / 1e9})
+        if 7 in cfgs:                      # the metric's "Loschmidt-echo steps/sec at D=2": cfg 3's grid with the reference's
+            NP, NT = int(4096 * args.scale), 1000     # own D = 2 ansatz (ShallowFullStateTensor, 15 parameters, represent.py:392-401)
+            rng = np.random.default_rng(7)
+            theta = torch.from_numpy(rng.normal(size=(NP, 15))).to(dev)
+            prog = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+            A0 = B.ansatz_tensors(prog, theta[:1], dtype=cdt)[0]
+            W = torch.from_numpy(np.stack([expm(-1j * Hamiltonian({'ZZ': -1, 'X': 0.2}).to_matrix() * 2 * 0.02 * k) for k in range(NT)])).to(dev).to(cdt)
+            from qmps_b200 import _lib as L_
+            for flag in (1, 0):
+                L_.load().qmps_set_option(b"fp_d2", flag)
+                med, best = timed(torch, lambda: B.loschmidt_costs(prog, theta, A0, W, dtype=cdt), args.reps, 1)
+                out.append({"cfg": 7, "dtype": tag, "what": "Loschmidt D=2 (4x4 mixed two-site map, all eigenvalues)", "NP": NP, "NT": NT,
+                            "kernel": "fp_d2_kernel (thread per problem)" if flag else "fixed_point_kernel<T,4> (generic)",
+                            "ms": med, "ms_best": best, "steps_per_s": NP * NT / med * 1e3})
+            L_.load().qmps_set_option(b"fp_d2", 1)
     for o in out:
         print(json.dumps(o))
 
