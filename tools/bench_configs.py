@@ -125,6 +125,15 @@ def main():
                             "kernel": "fp_d2_kernel (thread per problem)" if flag else "fixed_point_kernel<T,4> (generic)",
                             "ms": med, "ms_best": best, "steps_per_s": NP * NT / med * 1e3})
             L_.load().qmps_set_option(b"fp_d2", 1)
+        if 8 in cfgs:                      # D = 2 rotosolve: fused 3-shift energies for the reference's 15-parameter ansatz
+            N = int((1 << 20) * args.scale)
+            rng = np.random.default_rng(8)
+            theta = torch.from_numpy(rng.normal(size=(N, 15))).to(dev)
+            prog = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+            H = Hamiltonian({'ZZ': -1, 'X': 1.0}).to_matrix()
+            med, best = timed(torch, lambda: B.energy_theta(prog, theta, H, coord=7, shifts=B.ROTO3_SHIFTS, dtype=cdt), args.reps, 2)
+            out.append({"cfg": 8, "dtype": tag, "what": "rotosolve 3-shift energy D=2 (theta -> U -> A -> env -> energy, one launch)", "N": N,
+                        "evals": 3 * N, "ms": med, "ms_best": best, "evals_per_s": 3 * N / med * 1e3})
     for o in out:
         print(json.dumps(o))
 

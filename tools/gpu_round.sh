@@ -12,7 +12,7 @@ case $w in
 peaks) [ -x tools/peaks ] && timeout 120 tools/peaks > $OUT/peaks_$TAG.json 2> $OUT/peaks.err; cat $OUT/peaks_$TAG.json;;
 test) timeout 900 python -m pytest tests -m gpu -x -q --durations=5 > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu_$TAG.log
       tail -25 $OUT/pytest_gpu_$TAG.log;;
-configs) timeout 600 python tools/bench_configs.py --cfg 2,3,4,5,6 --c64 > $OUT/configs_$TAG.jsonl 2> $OUT/configs.err; echo "configs rc=$?"
+configs) timeout 600 python tools/bench_configs.py --cfg 2,3,4,5,6,7,8 --c64 > $OUT/configs_$TAG.jsonl 2> $OUT/configs.err; echo "configs rc=$?"
       cat $OUT/configs_$TAG.jsonl; tail -3 $OUT/configs.err;;
 bench) timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench.err;;
 sweep) timeout 300 python tools/sweep_d2.py > $OUT/sweep_d2_$TAG.jsonl 2> $OUT/sweep.err; cat $OUT/sweep_d2_$TAG.jsonl; tail -3 $OUT/sweep.err;;
