@@ -273,3 +273,156 @@ QMPS_HDN cx<T> bw_overlap(const Grp& g, const BwWork<T>& W, const cx<T>* Wop) {
 }
 
 }  // namespace qmps
+
+// ---- thread-per-candidate form of Evolve.exact_cost_function (:777-790) ---------------------------------
+// One ket state (U1, U2) and one W for a whole population of candidates (V1, V2) -- the TDVP optimiser's
+// use: chi = (1 (x) W (x) 1)|psi> is computed once per launch (64 amplitudes, shared), and the candidate's
+// work runs in registers: P = V1^dagger U1, the 4 x 4 right map, its eigenvalues (fp_d2.cuh), numpy's
+// complex-argmax selection, one inverse iteration in zgeev's gauge -> Mr, then the overlap contracted
+// left to right along the bra's matrix-product structure
+//   phi[q0,(q1q2),(q3q4),q5] = sum w2[q0,y1] U1_[(y1y2),(q1q2)] w2[y2,y3] U1_[(y3y4),(q3q4)] w2[y4,q5]
+// without ever forming the 64-amplitude bra (~450 complex MACs instead of ~2100 per candidate).
+#include "fp_d2.cuh"
+
+namespace qmps {
+
+// U1k: ket U1 [16], u2k: U2[:,0] [4], chi [64] (any address space; shared memory on the device).
+// V1, V2: the candidate's UNdaggered unitaries [16] each.  Returns the status of the eigen-solve.
+template <typename T>
+QMPS_HD int bw_cost_thread(const cx<T>* U1k, const cx<T>* u2k, const cx<T>* chi, const cx<T>* V1, const cx<T>* V2,
+                           cx<T>* overlap_out, cx<T>* lambda_out, cx<T>* Mr_out) {
+  // V1 is NOT held in registers across the eigen-solve (it would cost 64 of them): each stage reloads
+  // the four entries it needs (the candidate's 256 bytes stay in L1)
+  cx<T> w2[4], u2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { w2[q] = conj(V2[q * 4]); u2[q] = u2k[q]; }       // w2[2y+e] = U2_[0,(y,e)]
+  // right map E[(a,b),(c,e)] = sum_xy P[(b,y),(a,x)] u2[x,c] w2[y,e],  P = V1^dagger U1 (built entry by entry)
+  cx<T> E[4][4];
+  cx<T> lam = mk<T>(0, 0);
+  int status = ST_OK;
+  cx<T> mr[4];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) E[r][c] = mk<T>(0, 0);
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      cx<T> vcol[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) vcol[k] = V1[k * 4 + pr];
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        cx<T> pv = mk<T>(0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cmad_c(pv, U1k[k * 4 + pc], vcol[k]);          // conj(V1[k][pr]) U1[k][pc]
+        const int b = pr >> 1, y = pr & 1, a = pc >> 1, x = pc & 1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const cx<T> pu = pv * u2[2 * x + c];
+#pragma unroll
+          for (int ee = 0; ee < 2; ++ee) cmad(E[2 * a + b][2 * c + ee], pu, w2[2 * y + ee]);
+        }
+      }
+    }
+    if (pass == 0) {
+      cx<T> w[4];
+      status = fpd2_eigenvalues<T>(E, w);
+      int k = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        // numpy's complex argmax: lexicographic on (real, imag); the running best is selected by value
+        bool better = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j == k) better = w[i].re > w[j].re || (w[i].re == w[j].re && w[i].im > w[j].im);
+        if (better) k = i;
+      }
+      lam = w[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) if (i == k) lam = w[i];
+    } else {
+      fpd2_inverse_iteration<T>(E, lam, mr);
+      fpd2_fix_gauge<T>(mr, 1);
+    }
+  }
+  *lambda_out = lam;
+  if (Mr_out) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Mr_out[i] = mr[i];
+  }
+  // wl[x1,q0] = sum_q0' w2[q0',x1] Ml[q0',q0],  Ml = Mr^dagger: Ml[q0',q0] = conj(Mr[q0,q0'])
+  cx<T> wl[4];
+#pragma unroll
+  for (int x1 = 0; x1 < 2; ++x1)
+#pragma unroll
+    for (int q0 = 0; q0 < 2; ++q0) {
+      cx<T> s = mk<T>(0, 0);
+#pragma unroll
+      for (int qp = 0; qp < 2; ++qp) cmad_c(s, w2[2 * qp + x1], mr[2 * q0 + qp]);
+      wl[2 * x1 + q0] = s;
+    }
+  cx<T> S2[2][4][2];                                  // [x2][(q3q4)][q5']
+#pragma unroll
+  for (int x2 = 0; x2 < 2; ++x2)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int q5 = 0; q5 < 2; ++q5) S2[x2][g][q5] = mk<T>(0, 0);
+#pragma unroll 1
+  for (int h = 0; h < 4; ++h) {                       // h = (q1q2); rolled: bounds the live range of the chi / V1 loads
+    cx<T> uh[4];                                      // U1_[(x1x2),h] = conj(V1[h][(x1x2)])
+#pragma unroll
+    for (int q = 0; q < 4; ++q) uh[q] = conj(V1[h * 4 + q]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      cx<T> t[2][2], s1[2][2];                        // t[q0][q5'], s1[x1][q5']
+#pragma unroll
+      for (int q0 = 0; q0 < 2; ++q0) {
+        const cx<T> c0 = chi[(q0 << 5) | (h << 3) | (g << 1) | 0], c1 = chi[(q0 << 5) | (h << 3) | (g << 1) | 1];
+#pragma unroll
+        for (int q5 = 0; q5 < 2; ++q5) t[q0][q5] = mr[2 * q5] * c0 + mr[2 * q5 + 1] * c1;
+      }
+#pragma unroll
+      for (int x1 = 0; x1 < 2; ++x1)
+#pragma unroll
+        for (int q5 = 0; q5 < 2; ++q5) s1[x1][q5] = wl[2 * x1] * t[0][q5] + wl[2 * x1 + 1] * t[1][q5];
+#pragma unroll
+      for (int x1 = 0; x1 < 2; ++x1)
+#pragma unroll
+        for (int x2 = 0; x2 < 2; ++x2)
+#pragma unroll
+          for (int q5 = 0; q5 < 2; ++q5) cmad(S2[x2][g][q5], uh[2 * x1 + x2], s1[x1][q5]);
+    }
+  }
+  cx<T> S4[2][2];                                     // [x4][q5']
+#pragma unroll
+  for (int x4 = 0; x4 < 2; ++x4)
+#pragma unroll
+    for (int q5 = 0; q5 < 2; ++q5) S4[x4][q5] = mk<T>(0, 0);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    cx<T> ug[4];                                      // U1_[(x3x4),g] = conj(V1[g][(x3x4)])
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ug[q] = conj(V1[g * 4 + q]);
+#pragma unroll
+    for (int x3 = 0; x3 < 2; ++x3) {
+      cx<T> s3[2];                                    // S3[x3][g][q5'] = sum_x2 w2[x2,x3] S2[x2][g][q5']
+#pragma unroll
+      for (int q5 = 0; q5 < 2; ++q5) s3[q5] = w2[x3] * S2[0][g][q5] + w2[2 + x3] * S2[1][g][q5];
+#pragma unroll
+      for (int x4 = 0; x4 < 2; ++x4)
+#pragma unroll
+        for (int q5 = 0; q5 < 2; ++q5) cmad(S4[x4][q5], ug[2 * x3 + x4], s3[q5]);
+    }
+  }
+  cx<T> ov = mk<T>(0, 0);
+#pragma unroll
+  for (int x4 = 0; x4 < 2; ++x4)
+#pragma unroll
+    for (int q5 = 0; q5 < 2; ++q5) cmad(ov, w2[2 * x4 + q5], S4[x4][q5]);
+  *overlap_out = ov;
+  return status;
+}
+
+}  // namespace qmps

@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
@@ -126,6 +126,7 @@ int qmps_set_option(const char* name, int value) {
   if (!strcmp(name, "fp_block")) { g_options[OPT_FP_BLOCK] = value; return 0; }
   if (!strcmp(name, "er_wide")) { g_options[OPT_ER_WIDE] = value; return 0; }
   if (!strcmp(name, "fp_d2")) { g_options[OPT_FP_D2] = value; return 0; }
+  if (!strcmp(name, "bw_thread")) { g_options[OPT_BW_THREAD] = value; return 0; }
   return fail(QMPS_ERR_ARG, std::string("set_option: unknown option ") + name);
 }
 int qmps_debug_counters(unsigned long long* out4, int reset) {

@@ -29,6 +29,20 @@ int run_bw(const BwParams& p, int dtype, void* stream) {
 
 bool bcast_ok(int64_t n, int64_t N) { return n == 1 || n == N; }
 
+// one ket state, one W, many candidates: thread-per-candidate kernel behind a one-warp precompute of chi
+template <typename T> int launch_bw_cost_thread(const BwParams& p, cudaStream_t st) {
+  cx<T>* chi = nullptr;
+  CK(malloc_async((void**)&chi, sizeof(cx<T>) * 64, st));
+  bw_chi_kernel<T><<<1, 32, 0, st>>>((const cx<T>*)p.U1, (const cx<T>*)p.U2, (const cx<T>*)p.W, chi);
+  auto kern = bw_cost_thread_kernel<T>;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, 128, 0, (p.N + 127) / 128, &grid)) return rc;
+  kern<<<grid, 128, 0, st>>>(p, chi);
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(chi, st));
+  return 0;
+}
+
 int check_common(const char* who, int64_t N, int64_t NK, const void* U1, const void* U2, int dtype) {
   if (N < 0) return fail(QMPS_ERR_ARG, std::string(who) + ": negative batch");
   if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, std::string(who) + ": bad dtype");
@@ -108,6 +122,9 @@ int qmps_bw_evolve_cost(int64_t N, int64_t NK, const void* U1, const void* U2, i
   p.mode = BW_COST; p.bra_undaggered = 1; p.N = N; p.NK = NK; p.NB = NB; p.NW = NW;
   p.U1 = U1; p.U2 = U2; p.B1 = V1; p.B2 = V2; p.W = W; p.real_out = cost; p.overlap = overlap; p.eta = eta;
   p.vec = Mr; p.status = status;
+  if (NK == 1 && NW == 1 && option_get(OPT_BW_THREAD))
+    return dtype == QMPS_C128 ? launch_bw_cost_thread<double>(p, (cudaStream_t)stream)
+                              : launch_bw_cost_thread<float>(p, (cudaStream_t)stream);
   return run_bw(p, dtype, stream);
 }
 

@@ -120,7 +120,7 @@ int env_generic_f32(const EnvParams& p, int mode, cudaStream_t st) {
   return mode == 0 ? dispatch_env<0>(p, st) : dispatch_env<1>(p, st);
 }
 int fixed_point_f32(const FpParams& p, cudaStream_t st) {
-  if (p.D == 2 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
+  if (p.D == 2 && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
   // complex64, n = 16: 8 lanes per problem measured 24 % faster than 16 (profiles/sweep_fp_r01e.jsonl)
   if (p.D == 4 && (option_get(OPT_FP_GROUP) == 8 || option_get(OPT_FP_GROUP) == 0)) return launch_fp<8>(p, st);

@@ -129,7 +129,7 @@ int fp16_debug_f64(unsigned long long* out, int reset) {
   return 0;
 }
 int fixed_point_f64(const FpParams& p, cudaStream_t st) {
-  if (p.D == 2 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
+  if (p.D == 2 && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
   if (p.D == 4 && option_get(OPT_FP_GROUP) == 8) return launch_fp<8>(p, st);
   if (p.D == 4 && option_get(OPT_FP_GROUP) == 4) return launch_fp<4>(p, st);

@@ -159,6 +159,79 @@ template <typename T> QMPS_HD int fpd2_eigenvalues(cx<T> (&H)[4][4], cx<T> (&w)[
   return fail ? ST_NO_CONVERGE : ST_OK;
 }
 
+// One inverse iteration on (M - lambda) for the eigenvector, in registers: Gaussian elimination with
+// partial pivoting on the 4 x 5 augmented system (physical row swaps by predicated moves; same pivot
+// choice, tiny-pivot replacement and right-hand side as core.cuh::lu_solve_aug / generic.cuh::
+// leading_eigenpair).  M: the map (destroyed).  x: un-normalised solution.
+template <typename T> QMPS_HD void fpd2_inverse_iteration(cx<T> (&M)[4][4], cx<T> lam, cx<T> (&x)[4]) {
+  cx<T> rhs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    M[i][i] = M[i][i] - lam;
+    T t = T(0.61803398874989485) * T(i + 1);
+    t -= floor(t);
+    rhs[i] = mk<T>(T(0.5) + t, T(0.25) - T(0.5) * t);
+  }
+  T scale = cabs(lam);
+  if (!(scale > T(1e-30))) scale = T(1);
+  const T tiny = eps_of<T>::v() * scale;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int p = k;
+    T best = norm2(M[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 4; ++i) { const T a = norm2(M[i][k]); if (a > best) { best = a; p = i; } }
+#pragma unroll
+    for (int i = k + 1; i < 4; ++i) {
+      if (p == i) {
+#pragma unroll
+        for (int j = k; j < 4; ++j) { const cx<T> t = M[k][j]; M[k][j] = M[i][j]; M[i][j] = t; }
+        const cx<T> t = rhs[k]; rhs[k] = rhs[i]; rhs[i] = t;
+      }
+    }
+    cx<T> pv = M[k][k];
+    if (!(best >= tiny * tiny)) pv = mk<T>(tiny, 0);
+    M[k][k] = pv;
+    const cx<T> inv = cinv(pv);
+#pragma unroll
+    for (int i = k + 1; i < 4; ++i) {
+      const cx<T> f = M[i][k] * inv;
+#pragma unroll
+      for (int j = k + 1; j < 4; ++j) cmsub(M[i][j], f, M[k][j]);
+      cmsub(rhs[i], f, rhs[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    cx<T> acc = rhs[k];
+#pragma unroll
+    for (int j = k + 1; j < 4; ++j) cmsub(acc, M[k][j], x[j]);
+    x[k] = cdiv(acc, M[k][k]);
+  }
+}
+
+// unit 2-norm and a phase convention: gauge 0 = generic.cuh::leading_eigenpair (trace of the 2 x 2
+// reshape real non-negative; traceless: largest entry real positive), gauge 1 = zgeev /
+// scipy.linalg.eig (component of largest modulus real positive)
+template <typename T> QMPS_HD void fpd2_fix_gauge(cx<T> (&x)[4], int gauge) {
+  T nrm2 = T(0), bigv = T(-1);
+  cx<T> big = mk<T>(1, 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const T a = norm2(x[i]);
+    nrm2 += a;
+    if (a > bigv) { bigv = a; big = x[i]; }
+  }
+  const T inv = T(1) / sqrt(nrm2);
+  const cx<T> tr = x[0] + x[3];
+  cx<T> ph;
+  if (gauge == 0 && cabs(tr) * inv > T(1e-8)) ph = conj(tr) * (T(1) / cabs(tr));
+  else ph = conj(big) * (T(1) / sqrt(bigv));
+  ph = ph * inv;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = x[i] * ph;
+}
+
 // leading eigenvalue (largest modulus, first on ties -- core.cuh::argmax_abs) of a 4 x 4 map (destroyed)
 template <typename T> QMPS_HD int fpd2_leading_of(cx<T> (&E)[4][4], cx<T>* lambda_out) {
   cx<T> w[4];
@@ -174,10 +247,10 @@ template <typename T> QMPS_HD int fpd2_leading_of(cx<T> (&E)[4][4], cx<T>* lambd
   return status;
 }
 
-// the same from tensors A, B [d][2][2] (any address space); adjoint = 1: the left fixed point's map E^dagger
+// the same from tensors A, B [d][2][2] (any address space); adjoint = 1: the left fixed point's map
+// E^dagger.  vec (optional, 4 entries): the eigenvector, unit norm, gauge 0.
 template <typename T>
-QMPS_HD int fpd2_leading(const cx<T>* A, const cx<T>* B, int d, int adjoint, cx<T>* lambda_out) {
-  cx<T> E[4][4];
+QMPS_HD void fpd2_build(const cx<T>* A, const cx<T>* B, int d, int adjoint, cx<T> (&E)[4][4]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -188,7 +261,22 @@ QMPS_HD int fpd2_leading(const cx<T>* A, const cx<T>* B, int d, int adjoint, cx<
     for (int q = 0; q < 4; ++q) { a[q] = A[s * 4 + q]; b[q] = B[s * 4 + q]; }
     fpd2_accumulate<T>(E, a, b, adjoint);
   }
-  return fpd2_leading_of<T>(E, lambda_out);
+}
+
+template <typename T>
+QMPS_HD int fpd2_leading(const cx<T>* A, const cx<T>* B, int d, int adjoint, cx<T>* lambda_out, cx<T>* vec = nullptr) {
+  cx<T> E[4][4];
+  fpd2_build<T>(A, B, d, adjoint, E);
+  const int status = fpd2_leading_of<T>(E, lambda_out);
+  if (vec) {
+    fpd2_build<T>(A, B, d, adjoint, E);          // the QR iteration destroyed the map: rebuild (operands are cached)
+    cx<T> x[4];
+    fpd2_inverse_iteration<T>(E, *lambda_out, x);
+    fpd2_fix_gauge<T>(x, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vec[i] = x[i];
+  }
+  return status;
 }
 
 }  // namespace qmps

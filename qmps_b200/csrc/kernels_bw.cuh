@@ -108,4 +108,51 @@ bw_kernel(BwParams p) {
   }
 }
 
+// chi = (1 (x) W (x) 1)(1 (x) U1 (x) U1 (x) 1)(U2 (x) U2 (x) U2)|0..0>: once per launch of the thread-per-candidate
+// cost kernel (one warp, 64 amplitudes)
+template <typename T>
+__global__ void __launch_bounds__(32)
+bw_chi_kernel(const cx<T>* __restrict__ U1, const cx<T>* __restrict__ U2, const cx<T>* __restrict__ W,
+              cx<T>* __restrict__ chi) {
+  __shared__ cx<T> k1[16], k2[4], psi[64], tmp[64];
+  Grp g; g.lane = threadIdx.x; g.size = 32; g.mask = 0xffffffffu; g.cta = 0;
+  for (int e = g.lane; e < 16; e += 32) k1[e] = U1[e];
+  for (int q = g.lane; q < 4; q += 32) k2[q] = U2[q * 4];
+  g.sync();
+  bw_build_state<T>(g, k2, k1, 3, 0, psi, tmp);
+  bw_apply_mid<T>(g, W, 4, 6, psi, tmp);
+  g.sync();
+  for (int e = g.lane; e < 64; e += 32) chi[e] = tmp[e];
+}
+
+// Evolve.exact_cost_function for a population of candidates against ONE ket state and ONE W: a thread per
+// candidate, registers only (brickwall.cuh::bw_cost_thread); the shared ket data sit in shared memory and
+// are read as warp-wide broadcasts.  HBM traffic: the candidate's two unitaries in, one number out.
+template <typename T>
+__global__ void __launch_bounds__(128)
+bw_cost_thread_kernel(BwParams p, const cx<T>* __restrict__ chi_g) {
+  __shared__ cx<T> k1[16], k2[4], chi[64];
+  for (int e = threadIdx.x; e < 16; e += blockDim.x) k1[e] = reinterpret_cast<const cx<T>*>(p.U1)[e];
+  for (int q = threadIdx.x; q < 4; q += blockDim.x) k2[q] = reinterpret_cast<const cx<T>*>(p.U2)[q * 4];
+  for (int e = threadIdx.x; e < 64; e += blockDim.x) chi[e] = chi_g[e];
+  __syncthreads();
+  typedef cx<T> Z;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid < p.N; pid += stride) {
+    const Z* V1 = reinterpret_cast<const Z*>(p.B1) + (p.NB == 1 ? 0 : pid) * 16;
+    const Z* V2 = reinterpret_cast<const Z*>(p.B2) + (p.NB == 1 ? 0 : pid) * 16;
+    Z ov, lam, mr[4];
+    const int status = bw_cost_thread<T>(k1, k2, chi, V1, V2, &ov, &lam, mr);
+    if (p.real_out) reinterpret_cast<T*>(p.real_out)[pid] = -(ov.re * ov.re + ov.im * ov.im);
+    if (p.overlap) reinterpret_cast<Z*>(p.overlap)[pid] = ov;
+    if (p.eta) reinterpret_cast<Z*>(p.eta)[pid] = lam;
+    if (p.vec) {
+      Z* o = reinterpret_cast<Z*>(p.vec) + pid * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = mr[i];
+    }
+    if (p.status) p.status[pid] = status;
+  }
+}
+
 }  // namespace qmps

@@ -1,4 +1,4 @@
-// qmps_b200 D = 2 mixed fixed points, eigenvalue only: one THREAD per (A, B) pair, the 4 x 4 map and
+// qmps_b200 D = 2 mixed fixed points (eigenvalue, optionally the eigenvector): one THREAD per (A, B) pair, the 4 x 4 map and
 // its Hessenberg + QR iteration in registers (fp_d2.cuh).  This is the Loschmidt / TDVP-step cost
 // kernel of the D = 2 scripts (qmps/loschmidts/time_evo.py:75-116 = scripts/loschmidt.py:209-239,
 // qmps/time_evolve_tools.py:84-91): in the outer-product mode consecutive threads take consecutive
@@ -33,18 +33,30 @@ fp_d2_kernel(FpParams p) {
     const cx<T>* A = reinterpret_cast<const cx<T>*>(p.A) + ia * tsz;
     const cx<T>* B = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;
     cx<T> E[4][4];
+    auto build = [&]() {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) E[r][c] = mk<T>(0, 0);
-    for (int s = 0; s < d; ++s) {
-      cx<T> a[4], b[4];
+        for (int c = 0; c < 4; ++c) E[r][c] = mk<T>(0, 0);
+      for (int s = 0; s < d; ++s) {
+        cx<T> a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = ld_cx<T>(A + s * 4 + q); b[q] = ld_cx<T>(B + s * 4 + q); }
-      fpd2_accumulate<T>(E, a, b, p.left);
-    }
+        for (int q = 0; q < 4; ++q) { a[q] = ld_cx<T>(A + s * 4 + q); b[q] = ld_cx<T>(B + s * 4 + q); }
+        fpd2_accumulate<T>(E, a, b, p.left);
+      }
+    };
+    build();
     cx<T> lam;
     const int status = fpd2_leading_of<T>(E, &lam);
+    if (p.vec) {                                   // one inverse iteration on the rebuilt map (operands are in L1)
+      build();
+      cx<T> x[4];
+      fpd2_inverse_iteration<T>(E, lam, x);
+      fpd2_fix_gauge<T>(x, 0);
+      cx<T>* o = reinterpret_cast<cx<T>*>(p.vec) + pid * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = x[i];
+    }
     const T a2 = norm2(lam);
     if (p.eta) reinterpret_cast<cx<T>*>(p.eta)[pid] = lam;
     if (p.cost) reinterpret_cast<T*>(p.cost)[pid] = -sqrt(sqrt(a2));

@@ -266,11 +266,31 @@ int emu_brickwall(int mode, int side, int bra_undaggered, int mbits, int64_t N, 
 }
 
 // fp_d2.cuh: register-resident leading eigenvalue of the D = 2 mixed map (the thread body of fp_d2_kernel)
-int emu_fp_d2(int d, int64_t N, const double* A, const double* B, int left, double* eta, int32_t* status) {
+int emu_fp_d2(int d, int64_t N, const double* A, const double* B, int left, double* eta, int32_t* status, double* vec) {
   for (int64_t p = 0; p < N; ++p) {
     zc lam;
-    status[p] = fpd2_leading<double>((const zc*)A + p * (size_t)d * 4, (const zc*)B + p * (size_t)d * 4, d, left, &lam);
+    status[p] = fpd2_leading<double>((const zc*)A + p * (size_t)d * 4, (const zc*)B + p * (size_t)d * 4, d, left, &lam,
+                                     vec ? (zc*)vec + p * 4 : nullptr);
     eta[2 * p] = lam.re; eta[2 * p + 1] = lam.im;
+  }
+  return 0;
+}
+
+// brickwall.cuh::bw_cost_thread: the thread body of bw_cost_thread_kernel (one ket state, one W); chi is
+// built with the same group routines bw_chi_kernel runs
+int emu_bw_cost_thread(int64_t N, const double* U1, const double* U2, const double* V1, const double* V2,
+                       const double* Wop, double* cost, double* overlap, double* eta, double* Mr, int32_t* status) {
+  Grp g = solo();
+  zc k2[4], psi[64], tmp[64];
+  for (int q = 0; q < 4; ++q) k2[q] = ((const zc*)U2)[q * 4];
+  bw_build_state<double>(g, k2, (const zc*)U1, 3, 0, psi, tmp);
+  bw_apply_mid<double>(g, (const zc*)Wop, 4, 6, psi, tmp);
+  for (int64_t p = 0; p < N; ++p) {
+    zc ov, lam, mr[4];
+    status[p] = bw_cost_thread<double>((const zc*)U1, k2, tmp, (const zc*)V1 + p * 16, (const zc*)V2 + p * 16, &ov, &lam, mr);
+    cost[p] = -(ov.re * ov.re + ov.im * ov.im);
+    ((zc*)overlap)[p] = ov; ((zc*)eta)[p] = lam;
+    for (int i = 0; i < 4; ++i) ((zc*)Mr)[p * 4 + i] = mr[i];
   }
   return 0;
 }

@@ -156,6 +156,28 @@ def test_host_emu_of_device_algorithms_matches_reference_outputs(built, gold):
         assert same_up_to_phase(r["vec"][k], np.eye(2) / np.sqrt(2), 1e-9)
 
 
+def test_host_emu_thread_per_candidate_cost_matches_reference_outputs(built, gold):
+    """brickwall.cuh::bw_cost_thread (the thread body of bw_cost_thread_kernel: one ket state, one W,
+    registers only, bra contracted along its matrix-product structure) against the reference's own
+    Evolve.exact_cost_function outputs."""
+    lib, g = _emu(built), gold
+    lib.emu_bw_cost_thread.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 10
+    W = np.ascontiguousarray(g["W"])
+    for k in range(len(g["U1"])):
+        U1, U2 = np.ascontiguousarray(g["U1"][k]), np.ascontiguousarray(g["U2"][k])
+        V1 = np.ascontiguousarray(np.stack([g["V1"][k], g["U1"][k]]))          # the candidate, and the state itself
+        V2 = np.ascontiguousarray(np.stack([g["V2"][k], g["U2"][k]]))
+        cost = np.zeros(2); ov = np.zeros(2, complex); eta = np.zeros(2, complex)
+        Mr = np.zeros((2, 2, 2), complex); st = np.zeros(2, np.int32)
+        assert lib.emu_bw_cost_thread(2, _ptr(U1), _ptr(U2), _ptr(V1), _ptr(V2), _ptr(W), _ptr(cost), _ptr(ov), _ptr(eta),
+                                      _ptr(Mr), _ptr(st)) == 0
+        assert not st.any()
+        assert abs(cost[0] - g["exact_cost"][k]) < 1e-12 and abs(ov[0] - g["overlap"][k]) < 1e-11
+        assert abs(eta[0] - g["renv_eta"][k]) < 1e-12 and np.abs(Mr[0] - g["renv_vec"][k]).max() < 1e-10
+        c0, ov0, eta0, M0 = OB.bw_exact_cost(U1, U2, U1, U2, W)
+        assert abs(cost[1] - c0) < 1e-12 and abs(eta[1] - 1) < 1e-12 and same_up_to_phase(Mr[1], np.eye(2) / np.sqrt(2), 1e-9)
+
+
 # ------------------------------------------------------------------ GPU parity through the C ABI
 def _haar(n, count, seed):
     rs = np.random.RandomState(seed)
@@ -217,6 +239,16 @@ def test_gpu_brickwall_batch_vs_oracle_and_broadcast(built):
         assert abs(cost[k] - c0) < 1e-10 * max(1, abs(c0))
         assert abs(eta[k] - eta0) < 1e-11 and np.abs(Mr[k] - M0).max() < 1e-9
         assert abs(ov[k] - ov0) < 1e-9
+    # the same batch through the group kernel (thread-per-candidate path switched off)
+    lib = __import__("qmps_b200._lib", fromlist=["load"]).load()
+    lib.qmps_set_option(b"bw_thread", 0)
+    try:
+        cg = BW.bw_evolve_cost(U1, U2, V1, V2, W, want_all=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.qmps_set_option(b"bw_thread", 1)
+    assert (cg.cost - c.cost).abs().max().item() < 1e-12 and (cg.overlap - c.overlap).abs().max().item() < 1e-11
+    assert (cg.Mr - c.Mr).abs().max().item() < 1e-9 and int(cg.status.abs().sum()) == 0
     # complex64 mode: 1e-5
     c32 = BW.bw_evolve_cost(torch.from_numpy(U1).to(torch.complex64).cuda(), U2, V1, V2, W).cpu().numpy()
     assert c32.dtype == np.float32 and np.abs(c32 - cost).max() < 2e-5

@@ -243,15 +243,24 @@ def test_emu_fp_d2_register_eigenvalue_path(emu, left):
             A = np.stack([O.merge(a, a) for a in A])
             B = np.stack([O.merge(b, b) for b in B])
         A, B = np.ascontiguousarray(A), np.ascontiguousarray(B)
-        eta = np.zeros(N, complex); st = np.zeros(N, np.int32)
-        assert emu.emu_fp_d2(d, ctypes.c_int64(N), P(A), P(B), left, P(eta), P(st)) == 0
+        eta = np.zeros(N, complex); st = np.zeros(N, np.int32); vec = np.zeros((N, 2, 2), complex)
+        assert emu.emu_fp_d2(d, ctypes.c_int64(N), P(A), P(B), left, P(eta), P(st), P(vec)) == 0
         assert st.sum() == 0
         for k in range(N):
             E = O.transfer_matrix(A[k], B[k])
-            w = np.linalg.eigvals(E.conj().T if left else E)
+            Em = E.conj().T if left else E
+            w = np.linalg.eigvals(Em)
             w0 = w[np.argmax(np.abs(w))]
             assert abs(abs(eta[k]) - abs(w0)) < 1e-12
             assert np.abs(w - eta[k]).min() < 1e-11          # it IS an eigenvalue of the map
+            v = vec[k].reshape(-1)
+            ws = np.sort(np.abs(w))[::-1]
+            gap = max(np.abs(w - eta[k])[np.argsort(np.abs(w - eta[k]))[1]], 1e-3)
+            assert abs(np.linalg.norm(v) - 1) < 1e-12
+            assert np.abs(Em @ v - eta[k] * v).max() < 1e-11 / gap
+            x0, v0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], B[k])
+            if abs(eta[k] - x0) < 1e-9:                    # same eigenvalue picked: same gauge-fixed vector
+                assert np.abs(vec[k] - v0).max() < 1e-9 / gap
 
 
 def test_emu_ansatz_and_energy(emu):

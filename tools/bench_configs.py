@@ -104,12 +104,16 @@ def main():
             U1, U2, V1, V2 = haar(1), haar(1), haar(N), haar(N)
             h = np.random.default_rng(6).normal(size=(16, 16))
             W = torch.from_numpy(expm(-0.1j * (h + h.T))).to(dev).to(cdt)
-            med, best = timed(torch, lambda: BW.bw_evolve_cost(U1, U2, V1, V2, W), args.reps, 2)
-            # algorithmic work per candidate: W application 64 x 16 complex MACs + 4 gate layers of 64 x 4 + the
-            # 4x4 eigenproblem (~2e3) ~= 1.7e4 real flops; traffic 2 x 16 complex in, one real out
-            out.append({"cfg": 6, "dtype": tag, "what": "brick-wall Evolve.exact_cost_function (4x4 env eig + 6-qubit overlap)", "N": N,
-                        "ms": med, "ms_best": best, "costs_per_s": N / med * 1e3,
-                        "algo_gbs": N * (2 * 16 * (16 if cdt == torch.complex128 else 8) + (8 if cdt == torch.complex128 else 4)) / med * 1e3 / 1e9})
+            from qmps_b200 import _lib as L6
+            for flag in (1, 0):
+                L6.load().qmps_set_option(b"bw_thread", flag)
+                med, best = timed(torch, lambda: BW.bw_evolve_cost(U1, U2, V1, V2, W), args.reps, 2)
+                # traffic: 2 x 16 complex in, one real out per candidate
+                out.append({"cfg": 6, "dtype": tag, "what": "brick-wall Evolve.exact_cost_function (4x4 env eig + 6-qubit overlap)", "N": N,
+                            "kernel": "bw_cost_thread_kernel (thread per candidate)" if flag else "bw_kernel<T,16> (16 lanes per candidate)",
+                            "ms": med, "ms_best": best, "costs_per_s": N / med * 1e3,
+                            "algo_gbs": N * (2 * 16 * (16 if cdt == torch.complex128 else 8) + (8 if cdt == torch.complex128 else 4)) / med * 1e3 / 1e9})
+            L6.load().qmps_set_option(b"bw_thread", 1)
         if 7 in cfgs:                      # the metric's "Loschmidt-echo steps/sec at D=2": cfg 3's grid with the reference's
             NP, NT = int(4096 * args.scale), 1000     # own D = 2 ansatz (ShallowFullStateTensor, 15 parameters, represent.py:392-401)
             rng = np.random.default_rng(7)
