@@ -64,14 +64,17 @@ int launch_fp16(FpParams p, cudaStream_t st) {
 }
 
 // D = 2 eigenvalue-only path (kernels_fpd2.cuh): one thread per problem, registers only
-int launch_fp_d2(FpParams p, cudaStream_t st) {
-  auto kern = fp_d2_kernel<REAL>;
+template <bool VEC> int launch_fp_d2_v(FpParams p, cudaStream_t st) {
+  auto kern = fp_d2_kernel<REAL, VEC>;
   int grid = 1;
   if (int rc = persistent_grid(kern, 128, 0, (p.N + 127) / 128, &grid)) return rc;
   p.ws = nullptr; p.ws_stride = 0;
   kern<<<grid, 128, 0, st>>>(p);
   CK(cudaGetLastError());
   return 0;
+}
+int launch_fp_d2(const FpParams& p, cudaStream_t st) {
+  return p.vec ? launch_fp_d2_v<true>(p, st) : launch_fp_d2_v<false>(p, st);
 }
 
 template <int G> int launch_fp(FpParams p, cudaStream_t st) {

@@ -20,7 +20,9 @@ template <typename T> __device__ __forceinline__ cx<T> ld_cx(const cx<T>* p) {
   return mk<T>(v.x, v.y);
 }
 
-template <typename T>
+// VEC: also the eigenvector (a separate instantiation: the eigenvalue-only Loschmidt path keeps its
+// 112 registers)
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(128)
 fp_d2_kernel(FpParams p) {
   const int d = p.d;
@@ -48,7 +50,7 @@ fp_d2_kernel(FpParams p) {
     build();
     cx<T> lam;
     const int status = fpd2_leading_of<T>(E, &lam);
-    if (p.vec) {                                   // one inverse iteration on the rebuilt map (operands are in L1)
+    if (VEC && p.vec) {                            // one inverse iteration on the rebuilt map (operands are in L1)
       build();
       cx<T> x[4];
       fpd2_inverse_iteration<T>(E, lam, x);
