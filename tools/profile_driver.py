@@ -87,6 +87,16 @@ def main():
         W = haar(1, 16)[0].contiguous()
         for _ in range(args.reps):
             BW.bw_evolve_cost(U1, U2, V1, V2, W)
+    if "fpd2" in what:                    # the metric's D = 2 Loschmidt steps: thread-per-problem register kernel
+        NP, NT = 4096, 256
+        prog = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+        th = thetas(NP, 15)
+        A0 = B.ansatz_tensors(prog, th[:1])[0]
+        from scipy.linalg import expm
+        H = Hamiltonian({'ZZ': -1, 'X': 0.2}).to_matrix()
+        W = torch.from_numpy(np.stack([expm(-1j * H * 0.04 * k) for k in range(NT)])).to(dev)
+        for _ in range(args.reps):
+            B.loschmidt_costs(prog, th, A0, W)
     torch.cuda.synchronize()
     print("profile_driver done:", what)
 
