@@ -820,3 +820,99 @@ def test_imps_compat_loop_quantities(env):
     assert Map(AR[0], AR[0]).is_right_eigenvector(I) and Map(AR[0], AR[0]).is_left_eigenvector(l)
     eta, l2, r2 = TransferMatrix(AL[0]).eigs()
     assert abs(eta - 1) < 1e-10 and np.abs(r2 - r).max() < 1e-9 and abs(np.trace(l2 @ r2) - 1) < 1e-10
+
+
+# ---------------------------------------------------------------- BASELINE configs at FULL size: properties
+def _tfim_gates(NT, dt=0.02, g=0.2):
+    from scipy.linalg import expm
+    from qmps_b200.ground_state import Hamiltonian
+    H = Hamiltonian({'ZZ': -1, 'X': g}).to_matrix()
+    return np.stack([expm(-1j * H * 2 * dt * k) for k in range(NT)])
+
+
+@pytest.mark.parametrize("D,P,gate", [(4, 12, "cnot"), (2, 15, "full")])
+def test_loschmidt_full_size_properties(env, D, P, gate):
+    """BASELINE config 3 (D = 4) and its D = 2 twin at full size, 4096 parameter sets x 1000 times:
+    |eta| <= 1 everywhere, at t = 0 (W = 1) the cost of parameter set 0 against itself is exactly -1
+    and every other one is -sqrt(per-site fidelity) of the two states; sampled entries against the
+    oracle; statuses clean."""
+    t, B, O, R = env["torch"], env["B"], env["O"], env["R"]
+    NP, NT = 4096, 1000
+    theta = np.random.default_rng(2).normal(size=(NP, P))
+    prog = (R.ShallowCNOTStateTensor_nonuniform(4, np.zeros(P)) if gate == "cnot" else R.ShallowFullStateTensor(2, np.zeros(P))).program()
+    th = t.from_numpy(theta).cuda()
+    A0 = B.ansatz_tensors(prog, th[:1])[0]
+    W = _tfim_gates(NT)
+    cost, echo, eta = B.loschmidt_costs(prog, th, A0, t.from_numpy(W).cuda())
+    t.cuda.synchronize()
+    assert cost.shape == (NP, NT)
+    assert float(eta.abs().max()) <= 1 + 1e-10
+    assert abs(float(cost[0, 0]) + 1) < 1e-10
+    fid = B.overlap_theta(prog, th[:1].expand(NP, P).contiguous(), th).fid          # |eta(E_{A0 B_p})|^2
+    assert float((cost[:, 0] + fid.sqrt()).abs().max()) < 1e-9                     # two-site map at W = 1: eta_2 = eta^2, |eta_2| = fid
+    assert float((echo + 2 * t.log(-cost) * 2).abs().max()) < 1e-8                 # echo = -log|eta|^2, cost = -sqrt|eta|
+    A0n = A0.cpu().numpy()
+    rs = np.random.RandomState(0)
+    for _ in range(12):
+        p, k = int(rs.randint(NP)), int(rs.randint(NT))
+        Bp = B.ansatz_tensors(prog, th[p:p + 1])[0].cpu().numpy()
+        assert abs(float(cost[p, k]) - O.loschmidt_cost(A0n, Bp, W[k])) < TOL * 10
+
+
+def test_rotosolve_full_size_properties(env):
+    """BASELINE config 4 at full size (65536 parameter vectors, D = 8, 3 shifts on one coordinate): the
+    shift-0 column equals the plain energy, every energy lies inside the spectrum of the Heisenberg bond,
+    the closed-form coordinate update equals the reference formula on every vector and touches no other
+    coordinate, and the device argmin of the re-evaluated energies equals torch's."""
+    t, B, R = env["torch"], env["B"], env["R"]
+    from qmps_b200.ground_state import Hamiltonian
+    N, P, coord = 65536, 24, 5
+    theta = t.from_numpy(np.random.default_rng(3).normal(size=(N, P))).cuda()
+    prog = R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(P)).program()
+    H = Hamiltonian({'XX': 1, 'YY': 1, 'ZZ': 1}).to_matrix()
+    e3, st = B.energy_theta(prog, theta, H, coord=coord, shifts=B.ROTO3_SHIFTS, want_status=True)
+    e0 = B.energy_theta(prog, theta, H)
+    t.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    assert float((e3[:, 0] - e0).abs().max()) < 1e-11
+    w = np.linalg.eigvalsh(H)
+    assert float(e3.min()) >= w[0] - 1e-9 and float(e3.max()) <= w[-1] + 1e-9
+    # the closed-form coordinate update of qmps/rotosolve.py:175-177 on all 65536 vectors, against numpy.  (For an
+    # iMPS the energy is NOT a single sinusoid in one parameter -- the same gate sits on every site and in the
+    # environment -- so "theta* is the minimum" is not a property of the path; the reference applies the formula anyway.)
+    new = theta.clone()
+    B.rotosolve_fit(e3, new, coord)
+    e_new = B.energy_theta(prog, new, H)
+    e = e3.cpu().numpy()
+    wrap = lambda x: np.arctan2(np.sin(x), np.cos(x))                     # noqa: E731
+    step = wrap(-np.pi / 2 - np.arctan2(2 * e[:, 0] - e[:, 1] - e[:, 2], e[:, 1] - e[:, 2]))
+    want = wrap(theta[:, coord].cpu().numpy() + step)
+    assert np.abs(new[:, coord].cpu().numpy() - want).max() < 1e-12
+    changed = (new - theta).abs().sum(dim=1)
+    assert float((new - theta)[:, [c for c in range(P) if c != coord]].abs().max()) == 0 and float(changed.max()) > 0
+    bc, bi = B.argmin(e_new)
+    assert float(bc) == float(e_new.min()) and int(bi) == int(t.argmin(e_new))
+
+
+@pytest.mark.parametrize("dt_name", ["complex128", "complex64"])
+def test_tm_power_full_size_properties(env, dt_name):
+    """BASELINE config 5 at full size (D = 64 x 512 and D = 256 x 32 problems, K = 32): for A = B
+    left-canonical the Rayleigh quotient converges to 1, r stays unit-Frobenius and
+    Hermitian, and applying the map once more by an independent einsum reproduces eta r."""
+    t, B = env["torch"], env["B"]
+    cdt = getattr(t, dt_name)
+    tol = 1e-9 if cdt == t.complex128 else 2e-4
+    for D, N in ((64, 512), (256, 32)):
+        g = t.Generator(device="cuda").manual_seed(40 + D)
+        Z = t.randn((N, 2 * D, D), dtype=t.float64, device="cuda", generator=g) + 1j * t.randn((N, 2 * D, D), dtype=t.float64, device="cuda", generator=g)
+        Q, _ = t.linalg.qr(Z)
+        A = Q.reshape(N, D, 2, D).permute(0, 2, 1, 3).contiguous().to(cdt)
+        r, ray = B.tm_power(A, A, K=32)
+        t.cuda.synchronize()
+        assert float((t.linalg.matrix_norm(r) - 1).abs().max()) < tol * 10
+        assert float((r - r.conj().transpose(1, 2)).abs().max()) < tol * 10
+        assert float((ray - 1).abs().max()) < 1e-4                       # 32 applications of a gapped CPTP map
+        r64, A64 = r[:4].to(t.complex128), A[:4].to(t.complex128)
+        Er = t.einsum("nsij,njl,nskl->nik", A64, r64, A64.conj())
+        q = t.einsum("nij,nij->n", r64.conj(), Er)
+        assert float((q - ray[:4].to(t.complex128)).abs().max()) < tol * 10
