@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Tiny invocation of every kernel family, the target of compute-sanitizer runs:
+
+  compute-sanitizer --tool memcheck  python tools/sanitize_driver.py
+  compute-sanitizer --tool racecheck python tools/sanitize_driver.py
+
+Batches are a few dozen problems (odd sizes: ragged tails, idle sub-warp groups)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from scipy.linalg import expm
+    from qmps_b200 import batched as B, represent as R, brickwall as BW
+    from qmps_b200.ground_state import Hamiltonian
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(0)
+
+    def haar(n, m):
+        Z = rng.normal(size=(n, m, m)) + 1j * rng.normal(size=(n, m, m))
+        return np.ascontiguousarray(np.linalg.qr(Z)[0])
+
+    def tensors(n, D):
+        U = haar(n, 2 * D)
+        return torch.from_numpy(np.ascontiguousarray(U[:, :, :D].reshape(n, D, 2, D).transpose(0, 2, 1, 3))).to(dev)
+
+    H = Hamiltonian({'ZZ': -1, 'X': 0.7}).to_matrix()
+    for cdt in (torch.complex128, torch.complex64):
+        for D, n in ((2, 37), (4, 21), (8, 5), (16, 2)):
+            A, Bt = tensors(n, D).to(cdt), tensors(n, D).to(cdt)
+            B.env_exact(A=A)
+            B.env_exact(A=A * 0.9, assume_left_canonical=False)
+            B.fixed_point(A, Bt)
+            B.fixed_point(A, Bt, left=True, want_vec=False)
+            B.energy_tensor(A, H)
+            if D <= 8:
+                m = B.mixed_canonical(A * 0.8)
+                B.expectation_values(m.AL, np.stack([np.diag([1.0, -1.0]), np.array([[0, 1.0], [1.0, 0]])]))
+        for D, P, gate in ((2, 15, R.ShallowFullStateTensor), (4, 12, R.ShallowCNOTStateTensor_nonuniform),
+                           (8, 24, R.ShallowCNOTStateTensor_nonuniform)):
+            prog = gate(D, np.zeros(P)).program()
+            th = torch.from_numpy(rng.normal(size=(19, P))).to(dev)
+            e = B.energy_theta(prog, th, H, coord=1, shifts=B.ROTO3_SHIFTS, dtype=cdt)
+            B.rotosolve_fit(e.double(), th, 1)
+            A0 = B.ansatz_tensors(prog, th[:1], dtype=cdt)[0]
+            W = torch.from_numpy(np.stack([expm(-1j * H * 0.05 * k) for k in range(5)])).to(dev).to(cdt)
+            c = B.loschmidt_costs(prog, th, A0, W, dtype=cdt)[0]
+            B.argmin(c.double().reshape(-1))
+        U1, U2 = haar(1, 4)[0], haar(1, 4)[0]
+        V1, V2 = haar(23, 4), haar(23, 4)
+        Wb = haar(1, 16)[0]
+        z = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev).to(cdt)          # noqa: E731
+        BW.bw_evolve_cost(z(U1), z(U2), z(V1), z(V2), z(Wb), want_all=True)              # thread per candidate
+        BW.bw_evolve_cost(z(V1), z(V2), z(V1), z(V2), z(Wb), want_all=True)              # group kernel (NK = N)
+        BW.bw_environment(z(U1), z(U2), z(V1), z(V2), side="left", bra_undaggered=True)
+        BW.bw_expectation(z(V1), z(V2), z(Wb))
+        BW.bw_env_apply(z(U1), z(U2), z(V1), z(V2), z(haar(23, 2)))
+        for D, n in ((64, 3), (100, 2)):
+            A, Bt = tensors(n, D).to(cdt), tensors(n, D).to(cdt)
+            B.tm_power(A, Bt, 2)
+    B.loschmidt_rate(np.linspace(0.1, 2.0, 9), 1.5, 0.2)
+    torch.cuda.synchronize()
+    print("sanitize_driver done")
+
+
+if __name__ == "__main__":
+    main()
