@@ -26,6 +26,9 @@ Parity pinning status (see DESIGN.md section "Oracle"):
   ``tests/test_ground_state.py:101-102``, ``D2_gse`` of
   ``scripts/noisy_optimization.py:93``, the known-answer environment of
   ``new_tdvp/testTDVPStripped.py:156-170``.
+* PINNED, energy route: ``energy_of_unitary`` / ``energy_transfer`` against the reference's own cirq-free
+  script ``scripts/ground_state_finding.py:83-128`` run under stubs (``oracle/make_golden_gs.py`` ->
+  ``tests/golden/ref_ground_state_script.npz``; Pauli / CNOT matrices and ``TransferMatrix`` supplied).
 * PINNED, brick-wall family (``oracle/brickwall.py``): every function against outputs of the
   reference's unmodified ``new_tdvp/ClassicalTDVPStripped.py`` run under stub modules
   (``oracle/make_golden_bw.py`` -> ``tests/golden/ref_brickwall.npz``).

@@ -916,3 +916,25 @@ def test_tm_power_full_size_properties(env, dt_name):
         Er = t.einsum("nsij,njl,nskl->nik", A64, r64, A64.conj())
         q = t.einsum("nij,nij->n", r64.conj(), Er)
         assert float((q - ray[:4].to(t.complex128)).abs().max()) < tol * 10
+
+
+def test_energy_theta_against_reference_ground_state_script(env, golden):
+    """scripts/ground_state_finding.py:83-128 (the reference's cirq-free energy route) as a gate program:
+    Rx Rx / Rz Rz / CNOT layers.  The CUDA ansatz evaluator reproduces the script's unitaries (qubit order,
+    rotation conventions) and the fused energy kernel its energies, for 1, 2 and 4 layers."""
+    t, B, R, O = env["torch"], env["B"], env["R"], env["O"]
+    g = golden["ref_ground_state_script"]
+    for layers in (1, 2, 4):
+        P = 4 * layers
+        prog = R.GateProgram(2, P)
+        for l in range(layers):
+            prog.rx(0, 4 * l).rx(1, 4 * l + 1).rz(0, 4 * l + 2).rz(1, 4 * l + 3).cnot(0, 1)
+        theta = g[f"p_L{layers}"]
+        U = B.ansatz_unitaries_host(prog, theta)
+        assert np.abs(U[:, :, :2] - g[f"U_L{layers}"][:, :, :2]).max() < 1e-13      # the columns the tensor uses
+        assert np.abs(U - g[f"U_L{layers}"]).max() < 1e-13
+        for lam in (0.5, 1.0):
+            e = B.energy_theta(prog, theta, O.tfim_matrix(lam)).cpu().numpy()
+            assert np.abs(e - g[f"eps_L{layers}_lam{lam}"]).max() < 1e-10
+            e32 = B.energy_theta(prog, theta, O.tfim_matrix(lam), dtype=t.complex64).cpu().numpy()
+            assert np.abs(e32 - g[f"eps_L{layers}_lam{lam}"]).max() < 2e-5

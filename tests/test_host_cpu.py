@@ -338,3 +338,26 @@ def test_emu_canonical_forms_and_expectations(emu, D):
         ref = O.expectation_values(A[k], _PAULIS)
         assert np.abs(es[k] - ref).max() < 1e-10 and np.abs(es_gen[k] - ref).max() < 1e-10
         assert np.abs(es[k].imag).max() < 1e-12
+
+
+def test_emu_ansatz_and_energy_match_reference_ground_state_script(emu, golden):
+    """The device ansatz evaluator and D = 2 energy routine (compiled for the host) on the gate program of
+    scripts/ground_state_finding.py:83-92, against the tensors and energies of the reference's own script
+    (tests/golden/ref_ground_state_script.npz, oracle/make_golden_gs.py)."""
+    from qmps_b200 import represent as R
+    g = golden["ref_ground_state_script"]
+    for layers in (1, 2, 4):
+        Pn = 4 * layers
+        prog = R.GateProgram(2, Pn)
+        for l in range(layers):
+            prog.rx(0, 4 * l).rx(1, 4 * l + 1).rz(0, 4 * l + 2).rz(1, 4 * l + 3).cnot(0, 1)
+        for k in range(6):
+            th = np.ascontiguousarray(g[f"p_L{layers}"][k][None, :])
+            A = np.zeros((1, 2, 2, 2), complex)
+            emu.emu_ansatz_reg2(prog.c_ops(), len(prog), ctypes.c_int64(1), Pn, P(th), -1, ctypes.c_double(0.0), P(A))
+            assert np.abs(A[0] - O.unitary_to_tensor(g[f"U_L{layers}"][k])).max() < 1e-13
+            for lam in (0.5, 1.0):
+                H = np.ascontiguousarray(O.tfim_matrix(lam))
+                e = np.zeros(1)
+                emu.emu_energy_d2(ctypes.c_int64(1), P(A), P(H), P(e))
+                assert abs(e[0] - g[f"eps_L{layers}_lam{lam}"][k]) < 1e-11

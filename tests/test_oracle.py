@@ -188,3 +188,18 @@ def test_power_method_converges_to_fixed_point():
     r, q = O.power_method(A, A, 200)
     _, _, r0 = O.eigs(A)
     assert np.allclose(r / np.trace(r), r0, atol=1e-9) and abs(q - 1) < 1e-12
+
+
+def test_energy_chain_matches_reference_ground_state_script(golden):
+    """The reference's own cirq-free energy route (scripts/ground_state_finding.py:83-128: ansatz ->
+    get_env_exact -> state vector -> <1 x Ha x 1>), run under stubs by oracle/make_golden_gs.py: the
+    oracle's transfer-matrix energy and its state-vector energy of the script's unitaries reproduce the
+    script's numbers, and the oracle's TFIM matrix is the script's Ha."""
+    g = golden["ref_ground_state_script"]
+    assert np.abs(O.tfim_matrix(1.0) - g["Ha_1.0"]).max() < 1e-15
+    for layers in (1, 2, 4):
+        for lam in (0.5, 1.0):
+            H = O.tfim_matrix(lam)
+            for U, e_ref in zip(g[f"U_L{layers}"], g[f"eps_L{layers}_lam{lam}"]):
+                assert abs(O.energy_of_unitary(U, H) - e_ref) < 1e-11
+                assert abs(O.energy_transfer(O.unitary_to_tensor(U), H) - e_ref) < 1e-11
