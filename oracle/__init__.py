@@ -29,6 +29,9 @@ Parity pinning status (see DESIGN.md section "Oracle"):
 * PINNED, energy route: ``energy_of_unitary`` / ``energy_transfer`` against the reference's own cirq-free
   script ``scripts/ground_state_finding.py:83-128`` run under stubs (``oracle/make_golden_gs.py`` ->
   ``tests/golden/ref_ground_state_script.npz``; Pauli / CNOT matrices and ``TransferMatrix`` supplied).
+* PINNED, definitions cut out of reference modules with ``ast`` and executed unmodified
+  (``oracle/make_golden_misc.py`` -> ``tests/golden/ref_misc.npz``): ``merge``, ``put_env_on_*_site``,
+  ``get_env_off_*``, ``Hamiltonian.to_matrix``, ``rotosolve`` / ``double_rotosolve`` of qmps/rotosolve.py.
 * PINNED, brick-wall family (``oracle/brickwall.py``): every function against outputs of the
   reference's unmodified ``new_tdvp/ClassicalTDVPStripped.py`` run under stub modules
   (``oracle/make_golden_bw.py`` -> ``tests/golden/ref_brickwall.npz``).

@@ -938,3 +938,22 @@ def test_energy_theta_against_reference_ground_state_script(env, golden):
             assert np.abs(e - g[f"eps_L{layers}_lam{lam}"]).max() < 1e-10
             e32 = B.energy_theta(prog, theta, O.tfim_matrix(lam), dtype=t.complex64).cpu().numpy()
             assert np.abs(e32 - g[f"eps_L{layers}_lam{lam}"]).max() < 2e-5
+
+
+def test_dropin_time_evolve_tools_against_reference_functions(env, golden):
+    """qmps_b200.time_evolve_tools (merge and the environment embeddings, which complete their unitaries on
+    the GPU) against the reference's own functions cut out of qmps/time_evolve_tools.py:20-74
+    (tests/golden/ref_misc.npz)."""
+    from qmps_b200 import time_evolve_tools as TE
+    g = golden["ref_misc"]
+    for a, b, m in zip(g["merge_A"], g["merge_B"], g["merge_out"]):
+        assert np.abs(TE.merge(a, b) - m).max() < 1e-14
+    for k, q in enumerate(g["env_q"]):
+        UL, nL = TE.put_env_on_left_site(q, ret_n=True)
+        UR, nR = TE.put_env_on_right_site(q, ret_n=True)
+        assert abs(nL - g["left_n"][k]) < 1e-13 and abs(nR - g["right_n"][k]) < 1e-13
+        assert np.abs(TE.get_env_off_left_site(UL) - g["left_off"][k]).max() < 1e-12
+        assert np.abs(TE.get_env_off_right_site(UR) - g["right_off"][k]).max() < 1e-12
+        assert np.abs(UR[:2] - g["right_U"][k][:2]).max() < 1e-12                 # the defining rows are unique
+        for U in (UL, UR):
+            assert np.abs(U @ U.conj().T - np.eye(4)).max() < 1e-12

@@ -203,3 +203,54 @@ def test_energy_chain_matches_reference_ground_state_script(golden):
             for U, e_ref in zip(g[f"U_L{layers}"], g[f"eps_L{layers}_lam{lam}"]):
                 assert abs(O.energy_of_unitary(U, H) - e_ref) < 1e-11
                 assert abs(O.energy_transfer(O.unitary_to_tensor(U), H) - e_ref) < 1e-11
+
+
+def _state_function_of_make_golden_misc(p, *args):
+    from scipy.linalg import expm
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Y = np.array([[0, -1j], [1j, 0]]); Z = np.diag([1.0 + 0j, -1.0])
+    CN = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=complex)
+    psi = np.array([1, 0, 0, 0], dtype=complex)
+    for k in range(0, len(p), 4):
+        U = np.kron(expm(-0.5j * p[k] * Y), expm(-0.5j * p[k + 1] * Y))
+        V = np.kron(expm(-0.5j * p[k + 2] * Z), expm(-0.5j * p[k + 3] * X))
+        psi = V @ CN @ U @ psi
+    return psi
+
+
+def test_pure_functions_cut_out_of_reference_modules(golden):
+    """oracle/make_golden_misc.py executes, unmodified, function / class definitions cut out of reference
+    modules that cannot be imported whole: merge, put_env_on_{left,right}_site, get_env_off_*,
+    Hamiltonian.to_matrix.  The oracle restatements and the product's host-side mirror agree with them."""
+    g = golden["ref_misc"]
+    for a, b, m in zip(g["merge_A"], g["merge_B"], g["merge_out"]):
+        assert np.abs(O.merge(a, b) - m).max() < 1e-14
+    for k, q in enumerate(g["env_q"]):
+        UL, nL = O.put_env_on_left_site(q, ret_n=True)
+        UR, nR = O.put_env_on_right_site(q, ret_n=True)
+        assert abs(nL - g["left_n"][k]) < 1e-14 and abs(nR - g["right_n"][k]) < 1e-14
+        # the defining rows are unique; the null_space completion is not (compare what the call sites read)
+        assert np.abs(O.get_env_off_left_site(UL) - g["left_off"][k]).max() < 1e-13
+        assert np.abs(O.get_env_off_right_site(UR) - g["right_off"][k]).max() < 1e-13
+        assert np.abs(g["left_off"][k] * g["left_n"][k] - q).max() < 1e-13        # round trip of the reference itself
+        assert np.abs(g["right_off"][k] * g["right_n"][k] - q).max() < 1e-13
+        assert np.abs(UL @ UL.conj().T - np.eye(4)).max() < 1e-13 and np.abs(UR @ UR.conj().T - np.eye(4)).max() < 1e-13
+        assert np.abs(UR[:2] - g["right_U"][k][:2]).max() < 1e-13
+    assert np.abs(O.hamiltonian_to_matrix({'ZZ': -1, 'X': 0.7}) - g["H_tfim"]).max() < 1e-15
+    assert np.abs(O.hamiltonian_to_matrix({'XX': 1, 'YY': 1, 'ZZ': 1}) - g["H_heis"]).max() < 1e-15
+    assert np.abs(O.hamiltonian_to_matrix({'ZZ': -1.0, 'X': 0.3, 'IY': 0.25, 'ZI': -0.5, 'XY': 0.125}) - g["H_mixed"]).max() < 1e-15
+    from qmps_b200.ground_state import Hamiltonian
+    assert np.abs(Hamiltonian({'ZZ': -1.0, 'X': 0.3, 'IY': 0.25, 'ZI': -0.5, 'XY': 0.125}).to_matrix() - g["H_mixed"]).max() < 1e-15
+
+
+def test_rotosolve_drivers_match_reference_functions(golden):
+    """qmps/rotosolve.py:154-241 (`rotosolve`, `double_rotosolve`), cut out and run unmodified by
+    oracle/make_golden_misc.py on a deterministic state function: the product's host-side drivers
+    (qmps_b200/rotosolve.py) reproduce the energy histories and parameter trajectories."""
+    from qmps_b200 import rotosolve as RS
+    g = golden["ref_misc"]
+    es, S = RS.rotosolve(g["H_tfim"], _state_function_of_make_golden_misc, g["roto_p0"].copy(), N_iters=4)
+    assert np.abs(np.array(es) - g["roto_es"]).max() < 1e-10
+    assert np.abs(np.array(S) - g["roto_S"]).max() < 1e-9
+    es2, p2 = RS.double_rotosolve(g["H_tfim"], _state_function_of_make_golden_misc, g["roto_p0"].copy(), N_iters=3)
+    assert np.abs(es2 - g["droto_es"]).max() < 1e-7 and np.abs(p2 - g["droto_params"]).max() < 1e-5   # minimize_scalar tolerance
+    assert g["roto_es"][-1] <= g["roto_es"][0] + 1e-12
