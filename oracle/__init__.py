@@ -32,6 +32,9 @@ Parity pinning status (see DESIGN.md section "Oracle"):
 * PINNED, definitions cut out of reference modules with ``ast`` and executed unmodified
   (``oracle/make_golden_misc.py`` -> ``tests/golden/ref_misc.npz``): ``merge``, ``put_env_on_*_site``,
   ``get_env_off_*``, ``Hamiltonian.to_matrix``, ``rotosolve`` / ``double_rotosolve`` of qmps/rotosolve.py.
+* PINNED, ansatz gate lists: the reference's own ``_decompose_`` methods (qmps/represent.py:268-442) run
+  against a recording cirq stand-in (``oracle/make_golden_gates.py`` -> ``tests/golden/ref_gate_lists.json``);
+  the gate matrices themselves (cirq conventions) remain stated in ``oracle/gates.py``.
 * PINNED, brick-wall family (``oracle/brickwall.py``): every function against outputs of the
   reference's unmodified ``new_tdvp/ClassicalTDVPStripped.py`` run under stub modules
   (``oracle/make_golden_bw.py`` -> ``tests/golden/ref_brickwall.npz``).

@@ -361,3 +361,33 @@ def test_emu_ansatz_and_energy_match_reference_ground_state_script(emu, golden):
                 e = np.zeros(1)
                 emu.emu_energy_d2(ctypes.c_int64(1), P(A), P(H), P(e))
                 assert abs(e[0] - g[f"eps_L{layers}_lam{lam}"][k]) < 1e-11
+
+
+def test_gate_programs_match_reference_decompose_methods():
+    """Every ansatz class's GateProgram against the gate list its reference class's OWN ``_decompose_`` method
+    emits (qmps/represent.py:268-442 executed against a recording cirq stand-in by oracle/make_golden_gates.py):
+    same gates in the same order on the same qubits with the same angle / exponent."""
+    import json
+    from qmps_b200 import represent as R, _lib as L
+    names = {L.G_RZ: "rz", L.G_RX: "rx", L.G_RY: "ry", L.G_H: "H", L.G_CNOT: "CNOT", L.G_SWAP: "SWAP", L.G_CZ: "CZ",
+             L.G_XPOW: "X**", L.G_ZZPOW: "ZZ**", L.G_XXPOW: "XX**", L.G_YYPOW: "YY**", L.G_X: "X", L.G_Z: "Z"}
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_gate_lists.json")))
+    assert len(cases) >= 19
+    seen = set()
+    for c in cases:
+        p = np.array(c["params"])
+        gate = getattr(R, c["cls"])(*(([c["D"]] if c["D"] else []) + [p]))
+        prog = gate.program()
+        assert prog.nq == c["nq"], c["cls"]
+        ref_ops = [o for o in c["ops"] if not (o[0] == "SWAP" and o[1][0] == o[1][1])]
+        assert len(prog.ops) == len(ref_ops), (c["cls"], c["D"], len(prog.ops), len(ref_ops))
+        for (code, q0, q1, param, scale, offset), (name, qubits, value) in zip(prog.ops, ref_ops):
+            assert names[code] == name, (c["cls"], c["D"], names[code], name)
+            assert [q0, q1][:len(qubits)] == qubits or (len(qubits) == 1 and q0 == qubits[0]), (c["cls"], name, q0, q1, qubits)
+            if value is not None:
+                angle = scale * p[param] + offset
+                assert abs(angle - value) < 1e-15, (c["cls"], name, angle, value)
+            else:
+                assert param < 0
+        seen.add(c["cls"])
+    assert len(seen) == 8
