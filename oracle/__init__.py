@@ -35,6 +35,9 @@ Parity pinning status (see DESIGN.md section "Oracle"):
 * PINNED, ansatz gate lists: the reference's own ``_decompose_`` methods (qmps/represent.py:268-442) run
   against a recording cirq stand-in (``oracle/make_golden_gates.py`` -> ``tests/golden/ref_gate_lists.json``);
   the gate matrices themselves (cirq conventions) remain stated in ``oracle/gates.py``.
+* PINNED, Loschmidt / TDVP-step cost: the reference's own ``obj(p, A, WW)`` (qmps/loschmidts/time_evo.py:75-116)
+  executed unmodified on a minimal cirq stand-in with the oracle's xmps parts (``oracle/make_golden_obj.py`` ->
+  ``tests/golden/ref_loschmidt_obj.npz``).
 * PINNED, brick-wall family (``oracle/brickwall.py``): every function against outputs of the
   reference's unmodified ``new_tdvp/ClassicalTDVPStripped.py`` run under stub modules
   (``oracle/make_golden_bw.py`` -> ``tests/golden/ref_brickwall.npz``).

@@ -957,3 +957,23 @@ def test_dropin_time_evolve_tools_against_reference_functions(env, golden):
         assert np.abs(UR[:2] - g["right_U"][k][:2]).max() < 1e-12                 # the defining rows are unique
         for U in (UL, UR):
             assert np.abs(U @ U.conj().T - np.eye(4)).max() < 1e-12
+
+
+def test_dropin_loschmidt_obj_against_reference_function(env, golden):
+    """qmps_b200.loschmidts.time_evo.obj / obj_batched (ansatz -> merge -> D = 2 register eigen-solver, all on
+    the GPU) against the reference's own `obj(p, A, WW)` (qmps/loschmidts/time_evo.py:75-116) executed
+    unmodified by oracle/make_golden_obj.py."""
+    t = env["torch"]
+    from qmps_b200.loschmidts import time_evo as TE
+    g = golden["ref_loschmidt_obj"]
+    for a in range(len(g["A0"])):
+        cost, echo = TE.obj_batched(g["ps"], g["A0"][a], g["Ws"])
+        assert np.abs(cost.cpu().numpy() - g["obj"][a]).max() < 1e-10
+        assert np.abs(echo.cpu().numpy() + 4 * np.log(-g["obj"][a])).max() < 1e-8
+    assert abs(TE.obj(g["ps"][1], g["A0"][0], g["Ws"][1]) - g["obj"][0, 1, 1]) < 1e-10
+    # complex64 mode through the batched pipeline
+    from qmps_b200 import batched as B, represent as R
+    prog = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+    c32 = B.loschmidt_costs(prog, t.from_numpy(g["ps"]).cuda(), t.from_numpy(g["A0"][0]).cuda().to(t.complex64),
+                            t.from_numpy(g["Ws"]).cuda().to(t.complex64), dtype=t.complex64)[0]
+    assert np.abs(c32.cpu().numpy() - g["obj"][0]).max() < 1e-5

@@ -254,3 +254,19 @@ def test_rotosolve_drivers_match_reference_functions(golden):
     es2, p2 = RS.double_rotosolve(g["H_tfim"], _state_function_of_make_golden_misc, g["roto_p0"].copy(), N_iters=3)
     assert np.abs(es2 - g["droto_es"]).max() < 1e-7 and np.abs(p2 - g["droto_params"]).max() < 1e-5   # minimize_scalar tolerance
     assert g["roto_es"][-1] <= g["roto_es"][0] + 1e-12
+
+
+def test_loschmidt_cost_matches_reference_obj(golden):
+    """qmps/loschmidts/time_evo.py:75-116 `obj(p, A, WW)` executed unmodified (oracle/make_golden_obj.py: a minimal
+    state-vector stand-in for cirq, xmps parts from the oracle): the oracle's transfer-matrix cost -sqrt|eta_2| and
+    its own gate-by-gate 6-qubit circuit both reproduce the reference function's values."""
+    g = golden["ref_loschmidt_obj"]
+    for b in range(len(g["ps"])):
+        assert np.abs(O.shallow_full_state_tensor(g["ps"][b]) - g["U_gate"][b]).max() < 1e-13
+        B = O.left_canonicalise(O.unitary_to_tensor(g["U_gate"][b]))
+        for a in range(len(g["A0"])):
+            for w in range(len(g["Ws"])):
+                ref = g["obj"][a, b, w]
+                assert abs(O.loschmidt_cost(g["A0"][a], B, g["Ws"][w]) - ref) < 1e-10
+                assert abs(O.loschmidt_cost_circuit(g["A0"][a], B, g["Ws"][w]) - ref) < 1e-10
+    assert abs(g["obj"][0, 0, 0] + 1) < 1e-12
