@@ -3,7 +3,7 @@
 ``ast`` and executed unmodified, together with the helpers it calls from the same file (``merge``,
 ``put_env_on_left_site``, ``put_env_on_right_site``, ``gate``), ``Tensor`` / ``Environment`` /
 ``ShallowFullStateTensor`` from ``qmps/represent.py`` and ``unitary_to_tensor`` / ``tensor_to_unitary`` from the
-reference's ``qmps/tools.py``.
+reference's ``qmps/tools.py``; and ``get_overlap_exact(p1, p2)`` of ``qmps/time_evolve_tools.py:84-91`` likewise.
 
 What is NOT the reference's and is therefore stated here: a minimal state-vector stand-in for cirq (gate matrices
 in cirq's conventions, big-endian LineQubits, ``Circuit``, ``Simulator.simulate(...).final_state``, ``unitary``,
@@ -173,8 +173,19 @@ def main():
         for b in range(4):
             for w in range(3):
                 vals[a, b, w] = float(np.real(ns["obj"](ps[b], A0[a], Ws[w])))
+    # get_overlap_exact(p1, p2) of qmps/time_evolve_tools.py:84-91, same stand-ins (its `gate` default is the
+    # ShallowFullStateTensor factory of qmps/rotosolve.py:14-17, identical to time_evo.py's)
+    ns2 = dict(ns)
+    cut("qmps/time_evolve_tools.py", ["get_overlap_exact"], ns2)
+    ov = np.zeros((3, 4))
+    ov_r = np.zeros((3, 4, 2, 2), dtype=complex)
+    for a in range(3):
+        for b in range(4):
+            f, r = ns2["get_overlap_exact"](p0[a], ps[b])
+            ov[a, b], ov_r[a, b] = f, r
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "ref_loschmidt_obj.npz"), p0=p0, ps=ps, A0=A0, Ws=Ws, obj=vals,
+                        overlap=ov, overlap_r=ov_r,
                         U_gate=np.stack([unitary(ns["gate"](p)) for p in ps]))
     print("wrote ref_loschmidt_obj.npz", vals.shape, "obj(state itself, W=1) =", vals[0, 0, 0])
 

@@ -977,3 +977,22 @@ def test_dropin_loschmidt_obj_against_reference_function(env, golden):
     c32 = B.loschmidt_costs(prog, t.from_numpy(g["ps"]).cuda(), t.from_numpy(g["A0"][0]).cuda().to(t.complex64),
                             t.from_numpy(g["Ws"]).cuda().to(t.complex64), dtype=t.complex64)[0]
     assert np.abs(c32.cpu().numpy() - g["obj"][0]).max() < 1e-5
+
+
+def test_dropin_get_overlap_exact_against_reference_function(env, golden):
+    """qmps_b200.time_evolve_tools.get_overlap_exact (D = 2 register eigen-solver with eigenvector) against the
+    reference's own function (qmps/time_evolve_tools.py:84-91, oracle/make_golden_obj.py): the fidelity to 1e-10;
+    r is a right eigenvector of the mixed map (the reference's r is in xmps' gauge, supplied by the oracle)."""
+    from qmps_b200 import time_evolve_tools as TE
+    O = env["O"]
+    g = golden["ref_loschmidt_obj"]
+    for a in range(3):
+        for b in range(4):
+            f, r = TE.get_overlap_exact(g["p0"][a], g["ps"][b])
+            assert abs(f - g["overlap"][a, b]) < 1e-10
+            A = O.unitary_to_tensor(O.shallow_full_state_tensor(g["p0"][a]))
+            Bt = O.unitary_to_tensor(O.shallow_full_state_tensor(g["ps"][b]))
+            E = O.transfer_matrix(A, Bt)
+            v = np.asarray(r).reshape(-1)
+            lam = (v.conj() @ (E @ v)) / (v.conj() @ v)
+            assert abs(abs(lam) ** 2 - f) < 1e-9 and np.abs(E @ v - lam * v).max() < 1e-9

@@ -270,3 +270,14 @@ def test_loschmidt_cost_matches_reference_obj(golden):
                 assert abs(O.loschmidt_cost(g["A0"][a], B, g["Ws"][w]) - ref) < 1e-10
                 assert abs(O.loschmidt_cost_circuit(g["A0"][a], B, g["Ws"][w]) - ref) < 1e-10
     assert abs(g["obj"][0, 0, 0] + 1) < 1e-12
+
+
+def test_get_overlap_exact_matches_reference_function(golden):
+    """qmps/time_evolve_tools.py:84-91 executed unmodified (oracle/make_golden_obj.py): per-site fidelity
+    |eta(E_AB)|^2 of two parameter vectors; the oracle's restatement reproduces it, and the self-overlap is 1."""
+    g = golden["ref_loschmidt_obj"]
+    for a in range(3):
+        for b in range(4):
+            f, r = O.get_overlap_exact(g["p0"][a], g["ps"][b])
+            assert abs(f - g["overlap"][a, b]) < 1e-12
+    assert abs(g["overlap"][0, 0] - 1) < 1e-12
