@@ -320,7 +320,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                          "kernel": "env_d2_stream_kernel<false,false>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SOLVE * N,
-                         "kernel_ms": k_ms, "traffic": dram_traffic_from_profile()},
+                         "kernel_ms": k_ms, "traffic": dram_traffic_from_profile(),
+                         "traffic_note": "ncu --set full, one launch: DRAM reads 134.2 MB = the algorithmic 128 B/solve; "
+                                         "DRAM writes 38.5 MB < 83.9 MB algorithmic because part of the output is still "
+                                         "dirty in the 126 MB L2 when the launch ends (profiles/roofline_traffic.json)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * N, "d2h_bytes_per_step": 80 * N,
                     "steps": e2e_steps, "api": "qmps_env_exact_host (C ABI, pinned host buffers, chunked 3-stream pipeline)",
                     "link_bound_per_gpu": link_value,
