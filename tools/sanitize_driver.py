@@ -14,7 +14,41 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def reduced():
+    """The shared-memory group kernels only (the ones with intra-group barriers), three problems each: a racecheck
+    run of this finishes in minutes.  `python tools/sanitize_driver.py reduced`"""
+    import torch
+    from qmps_b200 import batched as B, brickwall as BW
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(0)
+
+    def haar(n, m):
+        Z = rng.normal(size=(n, m, m)) + 1j * rng.normal(size=(n, m, m))
+        return np.ascontiguousarray(np.linalg.qr(Z)[0])
+
+    def tensors(n, D):
+        U = haar(n, 2 * D)
+        return torch.from_numpy(np.ascontiguousarray(U[:, :, :D].reshape(n, D, 2, D).transpose(0, 2, 1, 3))).to(dev)
+    for D in (4, 8):
+        A, Bt = tensors(3, D), tensors(3, D)
+        B.fixed_point(A, Bt)                                 # Hessenberg + QR + inverse iteration, aliased scratch
+        B.fixed_point(A, Bt, left=True, want_vec=False)
+        B.env_exact(A=A * 0.9, assume_left_canonical=False)
+    A = tensors(3, 4)
+    m = B.mixed_canonical(A * 0.8)
+    B.expectation_values(m.AL, np.stack([np.diag([1.0, -1.0])]))
+    z = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)                      # noqa: E731
+    V1, V2 = haar(3, 4), haar(3, 4)
+    BW.bw_evolve_cost(z(V1), z(V2), z(V1[::-1].copy()), z(V2[::-1].copy()), z(haar(1, 16)[0]), want_all=True)   # group kernel
+    BW.bw_expectation(z(V1), z(V2), z(haar(1, 16)[0]))
+    torch.cuda.synchronize()
+    print("sanitize_driver (reduced) done")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "reduced":
+        return reduced()
     import torch
     from scipy.linalg import expm
     from qmps_b200 import batched as B, represent as R, brickwall as BW
