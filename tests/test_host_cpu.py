@@ -391,3 +391,14 @@ def test_gate_programs_match_reference_decompose_methods():
                 assert param < 0
         seen.add(c["cls"])
     assert len(seen) == 8
+
+
+def test_emu_fp_d2_edge_cases(emu):
+    """Degenerate inputs of the D = 2 register eigen-solver: the zero tensor (eta = 0), a product state (rank-one map,
+    eta = 1, eigenvector |0><0|) and NaN input (terminates, flagged QMPS_ST_NO_CONVERGE)."""
+    A = np.zeros((3, 2, 2, 2), complex); A[1, 0, 0, 0] = 1.0; A[2] = np.nan
+    eta = np.zeros(3, complex); st = np.zeros(3, np.int32); vec = np.zeros((3, 2, 2), complex)
+    assert emu.emu_fp_d2(2, ctypes.c_int64(3), P(A), P(A), 0, P(eta), P(st), P(vec)) == 0
+    assert eta[0] == 0 and st[0] == 0
+    assert abs(eta[1] - 1) < 1e-15 and st[1] == 0 and abs(vec[1, 0, 0] - 1) < 1e-12 and np.abs(vec[1]).sum() < 1 + 1e-9
+    assert np.isnan(eta[2].real) and st[2] == 2
