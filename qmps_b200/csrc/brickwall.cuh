@@ -426,3 +426,79 @@ QMPS_HD int bw_cost_thread(const cx<T>* U1k, const cx<T>* u2k, const cx<T>* chi,
 }
 
 }  // namespace qmps
+
+// ---- thread-per-problem form of exact_environment_circuit + exact_environment (:322-352, :394-426) ------------
+namespace qmps {
+
+// U1, U2: ket unitaries [16]; B1, B2: what the reference passes as U1_, U2_ (bra_undaggered = 0) or the candidate
+// unitaries themselves (1).  side 0 = right, 1 = left.  mat_out (optional, 16 entries): the 4 x 4 map.
+template <typename T>
+QMPS_HD int bw_env_thread(const cx<T>* U1, const cx<T>* U2, const cx<T>* B1, const cx<T>* B2, int bra_undaggered,
+                          int side, cx<T>* mat_out, cx<T>* lambda_out, cx<T>* vec_out) {
+  cx<T> u2[4], w2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { u2[q] = U2[q * 4]; w2[q] = bra_undaggered ? conj(B2[q * 4]) : B2[q]; }
+  cx<T> E[4][4];
+  cx<T> lam = mk<T>(0, 0);
+  int status = ST_OK;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) E[r][c] = mk<T>(0, 0);
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      cx<T> brow[4];                                   // row pr of U1_
+#pragma unroll
+      for (int k = 0; k < 4; ++k) brow[k] = bra_undaggered ? conj(B1[k * 4 + pr]) : B1[pr * 4 + k];
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        cx<T> pv = mk<T>(0, 0);                        // P[pr][pc] = sum_k U1_[pr][k] U1[k][pc]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cmad(pv, brow[k], U1[k * 4 + pc]);
+        // right: P[(b,y),(a,x)] u2[x,c] w2[y,e] -> E[(a,b),(c,e)];  left: P[(y,b),(x,a)] u2[c,x] w2[e,y]
+        const int r1 = pr >> 1, r0 = pr & 1, c1 = pc >> 1, c0 = pc & 1;
+        const int a = side == 0 ? c1 : c0, b = side == 0 ? r1 : r0, x = side == 0 ? c0 : c1, y = side == 0 ? r0 : r1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const cx<T> pu = pv * (side == 0 ? u2[2 * x + c] : u2[2 * c + x]);
+#pragma unroll
+          for (int ee = 0; ee < 2; ++ee) cmad(E[2 * a + b][2 * c + ee], pu, side == 0 ? w2[2 * y + ee] : w2[2 * ee + y]);
+        }
+      }
+    }
+    if (pass == 0) {
+      if (mat_out) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mat_out[r * 4 + c] = E[r][c];
+      }
+      cx<T> w[4];
+      status = fpd2_eigenvalues<T>(E, w);
+      int k = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        bool better = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j == k) better = w[i].re > w[j].re || (w[i].re == w[j].re && w[i].im > w[j].im);
+        if (better) k = i;
+      }
+      lam = w[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) if (i == k) lam = w[i];
+      *lambda_out = lam;
+      if (!vec_out) return status;
+    } else {
+      cx<T> x[4];
+      fpd2_inverse_iteration<T>(E, lam, x);
+      fpd2_fix_gauge<T>(x, 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vec_out[i] = x[i];
+    }
+  }
+  return status;
+}
+
+}  // namespace qmps

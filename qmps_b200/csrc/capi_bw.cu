@@ -43,6 +43,15 @@ template <typename T> int launch_bw_cost_thread(const BwParams& p, cudaStream_t 
   return 0;
 }
 
+template <typename T> int launch_bw_env_thread(const BwParams& p, cudaStream_t st) {
+  auto kern = bw_env_thread_kernel<T>;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, 128, 0, (p.N + 127) / 128, &grid)) return rc;
+  kern<<<grid, 128, 0, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int check_common(const char* who, int64_t N, int64_t NK, const void* U1, const void* U2, int dtype) {
   if (N < 0) return fail(QMPS_ERR_ARG, std::string(who) + ": negative batch");
   if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, std::string(who) + ": bad dtype");
@@ -66,6 +75,9 @@ int qmps_bw_environment(int side, int64_t N, int64_t NK, const void* U1, const v
   memset(&p, 0, sizeof(p));
   p.mode = BW_ENV; p.side = side; p.bra_undaggered = bra_undaggered; p.N = N; p.NK = NK; p.NB = NB;
   p.U1 = U1; p.U2 = U2; p.B1 = U1_; p.B2 = U2_; p.mat = mat; p.eta = eta; p.vec = vec; p.status = status;
+  if (option_get(OPT_BW_THREAD))
+    return dtype == QMPS_C128 ? launch_bw_env_thread<double>(p, (cudaStream_t)stream)
+                              : launch_bw_env_thread<float>(p, (cudaStream_t)stream);
   return run_bw(p, dtype, stream);
 }
 

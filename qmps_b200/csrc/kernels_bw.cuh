@@ -155,4 +155,29 @@ bw_cost_thread_kernel(BwParams p, const cx<T>* __restrict__ chi_g) {
   }
 }
 
+// exact_environment(_circuit) with a thread per problem (brickwall.cuh::bw_env_thread), any broadcast shape
+template <typename T>
+__global__ void __launch_bounds__(128)
+bw_env_thread_kernel(BwParams p) {
+  typedef cx<T> Z;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid < p.N; pid += stride) {
+    const Z* U1 = reinterpret_cast<const Z*>(p.U1) + (p.NK == 1 ? 0 : pid) * 16;
+    const Z* U2 = reinterpret_cast<const Z*>(p.U2) + (p.NK == 1 ? 0 : pid) * 16;
+    const Z* B1 = reinterpret_cast<const Z*>(p.B1) + (p.NB == 1 ? 0 : pid) * 16;
+    const Z* B2 = reinterpret_cast<const Z*>(p.B2) + (p.NB == 1 ? 0 : pid) * 16;
+    Z lam, x[4];
+    const int status = bw_env_thread<T>(U1, U2, B1, B2, p.bra_undaggered, p.side,
+                                        p.mat ? reinterpret_cast<Z*>(p.mat) + pid * 16 : nullptr, &lam,
+                                        p.vec ? x : nullptr);
+    if (p.eta) reinterpret_cast<Z*>(p.eta)[pid] = lam;
+    if (p.vec) {
+      Z* o = reinterpret_cast<Z*>(p.vec) + pid * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = x[i];
+    }
+    if (p.status) p.status[pid] = status;
+  }
+}
+
 }  // namespace qmps

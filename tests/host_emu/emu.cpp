@@ -295,4 +295,14 @@ int emu_bw_cost_thread(int64_t N, const double* U1, const double* U2, const doub
   return 0;
 }
 
+// brickwall.cuh::bw_env_thread: the thread body of bw_env_thread_kernel
+int emu_bw_env_thread(int side, int bra_undaggered, int64_t N, const double* U1, const double* U2, const double* B1,
+                      const double* B2, double* mat, double* eta, double* vec, int32_t* status) {
+  for (int64_t p = 0; p < N; ++p)
+    status[p] = bw_env_thread<double>((const zc*)U1 + p * 16, (const zc*)U2 + p * 16, (const zc*)B1 + p * 16,
+                                      (const zc*)B2 + p * 16, bra_undaggered, side, (zc*)mat + p * 16, (zc*)eta + p,
+                                      (zc*)vec + p * 4);
+  return 0;
+}
+
 }  // extern "C"

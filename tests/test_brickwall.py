@@ -178,6 +178,30 @@ def test_host_emu_thread_per_candidate_cost_matches_reference_outputs(built, gol
         assert abs(cost[1] - c0) < 1e-12 and abs(eta[1] - 1) < 1e-12 and same_up_to_phase(Mr[1], np.eye(2) / np.sqrt(2), 1e-9)
 
 
+def test_host_emu_thread_per_problem_environment_matches_reference_outputs(built, gold):
+    """brickwall.cuh::bw_env_thread (thread body of bw_env_thread_kernel): right / left exact environments in both
+    bra conventions against the reference's own outputs, and the same-state rank-one map (eta = 1, 1/sqrt 2)."""
+    lib, g = _emu(built), gold
+    lib.emu_bw_env_thread.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 8
+    c = lambda a: np.ascontiguousarray(a, dtype=np.complex128)          # noqa: E731
+    N = len(g["U1"])
+    U1, U2 = c(g["U1"]), c(g["U2"])
+    for side, undag, B1, B2, km, ke, kv in ((0, 0, c(dag(g["V1"])), c(dag(g["V2"])), "renv_mat", "renv_eta", "renv_vec"),
+                                            (1, 1, c(g["V1"]), c(g["V2"]), "lenv_mat", "lenv_eta", "lenv_vec"),
+                                            (0, 1, U1, U2, "renv_mat_same", "renv_eta_same", None)):
+        mat = np.zeros((N, 4, 4), complex); eta = np.zeros(N, complex); vec = np.zeros((N, 2, 2), complex)
+        st = np.zeros(N, np.int32)
+        assert lib.emu_bw_env_thread(side, undag, N, _ptr(U1), _ptr(U2), _ptr(B1), _ptr(B2), _ptr(mat), _ptr(eta),
+                                     _ptr(vec), _ptr(st)) == 0
+        assert not st.any()
+        assert np.abs(mat - g[km]).max() < 1e-13 and np.abs(eta - g[ke]).max() < 1e-12
+        if kv:
+            assert np.abs(vec - g[kv]).max() < 1e-10
+        else:
+            for k in range(N):
+                assert same_up_to_phase(vec[k], np.eye(2) / np.sqrt(2), 1e-9)
+
+
 # ------------------------------------------------------------------ GPU parity through the C ABI
 def _haar(n, count, seed):
     rs = np.random.RandomState(seed)
