@@ -32,6 +32,16 @@ UNIT = "solves/s"
 WORKLOAD = "exact_env_D2_d2_c128_2^20_per_gpu"
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line: to the real stdout saved by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -143,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -335,7 +345,7 @@ def run_ours(args):
             rate, cores, _ = cpu_reference_rate(per_core=2048, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"2048 per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -350,10 +360,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time direct launches only (no CUDA-graph replay)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." at
+    # communicator creation, torchrun children inherit the descriptor): keep the real stdout aside for the JSON
+    # line and point descriptor 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _JSON_OUT.flush()
 
 
 if __name__ == "__main__":
