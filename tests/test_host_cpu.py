@@ -402,3 +402,30 @@ def test_emu_fp_d2_edge_cases(emu):
     assert eta[0] == 0 and st[0] == 0
     assert abs(eta[1] - 1) < 1e-15 and st[1] == 0 and abs(vec[1, 0, 0] - 1) < 1e-12 and np.abs(vec[1]).sum() < 1 + 1e-9
     assert np.isnan(eta[2].real) and st[2] == 2
+
+
+def test_c_abi_argument_validation_without_a_device(built):
+    """Error behaviour of the C ABI: invalid arguments are rejected with a negative code and a
+    message BEFORE any CUDA call, so this runs on the GPU-less container too; empty batches are a no-op success."""
+    from qmps_b200 import _lib as L
+    lib = L.load()
+    ERR_ARG, ERR_UNSUPPORTED = -1, -3
+    cases = [
+        (lib.qmps_fixed_point(2, 3, 1, 1, 1, 1, 0, 0, None, None, None, None, None, None, L.C128, None), ERR_UNSUPPORTED, "D must be"),
+        (lib.qmps_fixed_point(2, 2, 2, 1, 3, 1, 0, 0, None, None, None, None, None, None, L.C128, None), ERR_ARG, "broadcast"),
+        (lib.qmps_fixed_point(2, 2, 1, 1, 1, 1, 0, 0, None, None, None, None, None, None, 7, None), ERR_ARG, "dtype"),
+        (lib.qmps_tm_power(2, 4, 1, None, None, None, 1, None, L.C128, None), ERR_ARG, "tm_power"),
+        (lib.qmps_bw_evolve_cost(4, 3, 1, 1, 4, 1, 1, 1, 1, 1, None, None, None, None, L.C128, None), ERR_ARG, "NK must be 1 or N"),
+        (lib.qmps_bw_environment(2, 1, 1, 1, 1, 1, 1, 1, 0, None, None, None, None, L.C128, None), ERR_ARG, "side"),
+        (lib.qmps_bw_expectation(1, 1, 1, 1, 3, 1, 1, 1, L.C128, None), ERR_UNSUPPORTED, "2 or 4 qubits"),
+        (lib.qmps_cgemm_c64_tc(1, 1, 60, 64, 32, 1, 1, 0, 1, None), ERR_UNSUPPORTED, "multiples of 64"),
+        (lib.qmps_set_option(b"no_such_option", 1), ERR_ARG, "unknown option"),
+    ]
+    for rc, want, msg in cases:
+        assert rc == want, (rc, want, msg)
+    assert lib.qmps_set_option(b"no_such_option", 1) == ERR_ARG and b"unknown option" in lib.qmps_last_error()
+    # empty batches succeed without touching the device
+    assert lib.qmps_fixed_point(2, 2, 0, None, 0, None, 0, 0, None, None, None, None, None, None, L.C128, None) == 0
+    assert lib.qmps_tm_power(2, 64, 0, None, None, None, 4, None, L.C64, None) == 0
+    assert lib.qmps_bw_evolve_cost(0, 1, None, None, 0, None, None, 1, None, None, None, None, None, None, L.C128, None) == 0
+    assert lib.qmps_env_exact(2, 2, 0, None, 0, 1, None, None, None, None, L.C128, None) == 0
