@@ -119,14 +119,23 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None):
+def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None, budget_s=None):
     """Per-call reference path (qmps/tools.py:176-182 restated in oracle/) on all host cores.
-    Returns (solves/s, cores, seconds per step)."""
+    per_core = None: sized from a calibration on the warmed-up pool so that warmup + steps maps take about
+    `budget_s` seconds (clamped to 128 .. 1024 solves per core per step).
+    Returns (solves/s, cores, seconds per step, per_core)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores) as pool:
+        if per_core is None:
+            pool.map(_cpu_worker, [(c, 32) for c in range(cores)])              # imports, page-in
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(1000 + c, 128) for c in range(cores)])
+            per_core_rate = 128 / (time.perf_counter() - t0)
+            per_core = int(budget_s * per_core_rate / max(1, steps + warmup))
+            per_core = max(128, min(1024, per_core))
         for s in range(warmup + steps):
             t0 = time.perf_counter()
             pool.map(_cpu_worker, [(s * cores + c, per_core) for c in range(cores)])
@@ -134,15 +143,17 @@ def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None):
             if s >= warmup:
                 times.append(dt)
     total = sum(times)
-    return per_core * cores * len(times) / total, cores, total / len(times)
+    return per_core * cores * len(times) / total, cores, total / len(times), per_core
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    per_core = 1024
-    rate, cores, sec = cpu_reference_rate(per_core, steps=args.steps, warmup=min(args.warmup, 2))
+    # each step is a bounded sample of the 2^20-solve workload, sized so that the WHOLE --steps K --warmup W run
+    # stays near two minutes whatever K is: a calibration on the warmed-up pool gives the per-core rate
+    warm = min(args.warmup, 2)
+    rate, cores, sec, per_core = cpu_reference_rate(None, steps=args.steps, warmup=warm, budget_s=120.0)
     sample = f"{per_core} per-call get_env_exact solves per core per step on {cores} cores (oracle port of qmps/tools.py:176-182; numpy eig + scipy cholesky + null_space)"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -342,7 +353,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            rate, cores, _ = cpu_reference_rate(per_core=2048, steps=1, warmup=0)
+            rate, cores, _, _ = cpu_reference_rate(per_core=2048, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"2048 per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
         emit(line)
