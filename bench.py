@@ -353,9 +353,10 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            rate, cores, _, _ = cpu_reference_rate(per_core=2048, steps=1, warmup=0)
+            # a bounded sample: one untimed warm-up map (imports, page-in), then ~15 s of per-call solves
+            rate, cores, _, pc = cpu_reference_rate(per_core=None, steps=4, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"2048 per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
+                                    "sample": f"4 x {pc} per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
         emit(line)
     if world > 1:
         dist.barrier()
