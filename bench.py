@@ -119,10 +119,10 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None, budget_s=None):
+def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None, budget_s=None, max_per_core=1024):
     """Per-call reference path (qmps/tools.py:176-182 restated in oracle/) on all host cores.
     per_core = None: sized from a calibration on the warmed-up pool so that warmup + steps maps take about
-    `budget_s` seconds (clamped to 128 .. 1024 solves per core per step).
+    `budget_s` seconds (clamped to 128 .. max_per_core solves per core per step).
     Returns (solves/s, cores, seconds per step, per_core)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
@@ -135,7 +135,7 @@ def cpu_reference_rate(per_core, steps=1, warmup=0, cores=None, budget_s=None):
             pool.map(_cpu_worker, [(1000 + c, 128) for c in range(cores)])
             per_core_rate = 128 / (time.perf_counter() - t0)
             per_core = int(budget_s * per_core_rate / max(1, steps + warmup))
-            per_core = max(128, min(1024, per_core))
+            per_core = max(128, min(max_per_core, per_core))
         for s in range(warmup + steps):
             t0 = time.perf_counter()
             pool.map(_cpu_worker, [(s * cores + c, per_core) for c in range(cores)])
@@ -354,7 +354,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             # a bounded sample: one untimed warm-up map (imports, page-in), then ~15 s of per-call solves
-            rate, cores, _, pc = cpu_reference_rate(per_core=None, steps=4, warmup=1, budget_s=15.0)
+            rate, cores, _, pc = cpu_reference_rate(per_core=None, steps=4, warmup=1, budget_s=15.0, max_per_core=16384)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"4 x {pc} per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
         emit(line)
