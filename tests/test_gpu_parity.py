@@ -996,3 +996,25 @@ def test_dropin_get_overlap_exact_against_reference_function(env, golden):
             v = np.asarray(r).reshape(-1)
             lam = (v.conj() @ (E @ v)) / (v.conj() @ v)
             assert abs(abs(lam) ** 2 - f) < 1e-9 and np.abs(E @ v - lam * v).max() < 1e-9
+
+
+def test_torch_library_ops_match_batched_api(env):
+    """The torch.library layer (qmps_b200/ops.py) returns exactly what the batched API returns."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    import qmps_b200.ops  # noqa: F401
+    from qmps_b200 import brickwall as BW
+    A = t.from_numpy(tensors(4, 9, 61, O)).cuda()
+    Bt = t.from_numpy(tensors(4, 5, 62, O)).cuda()
+    eta, r, C, st = t.ops.qmps_b200.env_exact(A)
+    ref = B.env_exact(A=A)
+    assert t.equal(r, ref.r) and t.equal(C, ref.C) and t.equal(eta, ref.eta) and t.equal(st, ref.status)
+    e2, cost, echo, fid = t.ops.qmps_b200.fixed_point_cost(A, Bt, True)
+    fp = B.fixed_point(A, Bt, pair="outer", want_vec=False)
+    assert cost.shape == (9, 5) and t.equal(cost, fp.cost) and t.equal(fid, fp.fid)
+    rK, ray = t.ops.qmps_b200.tm_power(A, A, 3)
+    r2, ray2 = B.tm_power(A, A, 3)
+    assert t.equal(rK, r2) and t.equal(ray, ray2)
+    U = t.from_numpy(haar_batch(4, 6, 71)).cuda()
+    W = t.from_numpy(haar_batch(16, 1, 72)[0]).cuda()
+    c = t.ops.qmps_b200.bw_evolve_cost(U[0], U[1], U[2:], U[2:].flip(0).contiguous(), W)
+    assert t.equal(c, BW.bw_evolve_cost(U[0], U[1], U[2:], U[2:].flip(0).contiguous(), W))

@@ -429,3 +429,26 @@ def test_c_abi_argument_validation_without_a_device(built):
     assert lib.qmps_tm_power(2, 64, 0, None, None, None, 4, None, L.C64, None) == 0
     assert lib.qmps_bw_evolve_cost(0, 1, None, None, 0, None, None, 1, None, None, None, None, None, None, L.C128, None) == 0
     assert lib.qmps_env_exact(2, 2, 0, None, 0, 1, None, None, None, None, L.C128, None) == 0
+
+
+def test_torch_library_ops_registered_cuda_only(built):
+    """qmps_b200/ops.py: the custom ops exist, have shape functions (trace as opaque nodes under FakeTensorMode) and
+    have NO CPU implementation -- a CPU tensor raises instead of falling back."""
+    import torch
+    import qmps_b200.ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("env_exact", "fixed_point_cost", "tm_power", "bw_evolve_cost"):
+        assert hasattr(torch.ops.qmps_b200, name)
+    with pytest.raises(NotImplementedError):
+        torch.ops.qmps_b200.env_exact(torch.zeros(1, 2, 2, 2, dtype=torch.complex128))
+    with pytest.raises(NotImplementedError):
+        torch.ops.qmps_b200.tm_power(torch.zeros(1, 2, 4, 4, dtype=torch.complex64), torch.zeros(1, 2, 4, 4, dtype=torch.complex64), 2)
+    with FakeTensorMode():
+        A = torch.empty((5, 2, 4, 4), dtype=torch.complex128, device="cuda")
+        eta, r, C, st = torch.ops.qmps_b200.env_exact(A)
+        assert tuple(r.shape) == (5, 4, 4) and st.dtype == torch.int32 and eta.dtype == torch.complex128
+        e2, cost, echo, fid = torch.ops.qmps_b200.fixed_point_cost(A, A[:3], True)
+        assert tuple(cost.shape) == (5, 3) and cost.dtype == torch.float64
+        V = torch.empty((7, 4, 4), dtype=torch.complex64, device="cuda")
+        c = torch.ops.qmps_b200.bw_evolve_cost(V[:1], V[:1], V, V, torch.empty((16, 16), dtype=torch.complex64, device="cuda"))
+        assert tuple(c.shape) == (7,) and c.dtype == torch.float32
