@@ -452,3 +452,20 @@ def test_torch_library_ops_registered_cuda_only(built):
         V = torch.empty((7, 4, 4), dtype=torch.complex64, device="cuda")
         c = torch.ops.qmps_b200.bw_evolve_cost(V[:1], V[:1], V, V, torch.empty((16, 16), dtype=torch.complex64, device="cuda"))
         assert tuple(c.shape) == (7,) and c.dtype == torch.float32
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_json_line():
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1: rank 0 alone runs and prints
+    exactly ONE JSON line on stdout carrying the contract's keys; the other rank exits 0 silently."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29619", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "solves/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
