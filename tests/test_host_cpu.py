@@ -469,3 +469,20 @@ def test_bench_reference_arm_under_torchrun_prints_one_json_line():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "solves/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_header_is_plain_c_and_library_binds_from_c(built, tmp_path):
+    """include/qmps_b200.h compiles as C99 (and as C++), and a C client can dlopen the library, resolve the
+    symbols and get the documented error behaviour -- what a cgo / JNI / FFI stub on the reference side would do."""
+    from qmps_b200 import _lib
+    hdr = os.path.join(ROOT, "include", "qmps_b200.h")
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        lang = ["-x", "c"] if cc == "gcc" else ["-x", "c++"]
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", *lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    exe = tmp_path / "c_client"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-o", str(exe), os.path.join(ROOT, "tests", "c_abi", "c_client.c"), "-ldl"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0 and "c_client ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
