@@ -1,6 +1,7 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, benches, D=2 sweep, ncu captures.
 # Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh [tag] [what...]
+#   what: peaks test configs bench sweep launches ncu ncutc smoke cpu dist memcheck racecheck ncuthread
 TAG=${1:-r01}; shift
 WHAT=${@:-"test configs bench sweep ncu"}
 OUT=gpurun_out
@@ -24,6 +25,13 @@ ncu) timeout 300 ncu --set full --clock-control none --import-source on -k regex
       python tools/profile_driver.py --what fp4,en8,pw64 --reps 1 > $OUT/ncu_generic.log 2>&1;;
 ncutc) timeout 300 ncu --set full --clock-control none --import-source on -k regex:'cgemm_tc_kernel|gauge_kernel|expect_kernel|fp16_kernel' -c 6 -f -o $OUT/prof_tc_$TAG \
       python tools/profile_driver.py --what tc64,tc256,fp4,canon --reps 1 > $OUT/ncu_tc.log 2>&1; tail -3 $OUT/ncu_tc.log;;
+smoke) timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log;;
+cpu) timeout 200 python tools/cpu_baselines.py --seconds 3 > $OUT/cpu_baselines_$TAG.jsonl 2> $OUT/cpu_baselines.err; cut -c1-160 $OUT/cpu_baselines_$TAG.jsonl;;
+dist) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > $OUT/dist_check_$TAG.json 2> $OUT/dist_check.err; cat $OUT/dist_check_$TAG.json;;
+memcheck) timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_driver.py > $OUT/sanitize_memcheck_$TAG.log 2>&1; tail -3 $OUT/sanitize_memcheck_$TAG.log;;
+racecheck) timeout 330 compute-sanitizer --tool racecheck --print-limit 30 python tools/sanitize_driver.py reduced > $OUT/sanitize_racecheck_$TAG.log 2>&1; tail -3 $OUT/sanitize_racecheck_$TAG.log;;
+ncuthread) timeout 200 ncu --set full --clock-control none --import-source on -k regex:'fp_d2_kernel|bw_cost_thread_kernel' -c 2 -f -o $OUT/prof_thread_$TAG \
+      python tools/profile_driver.py --what fpd2,bw --reps 1 > $OUT/ncu_thread.log 2>&1; tail -2 $OUT/ncu_thread.log;;
 esac
 done
 ls -la $OUT | tail -30
