@@ -120,13 +120,23 @@ int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_
  *     pair_mode 0: problem i uses A[min(i,NA-1)] , B[min(i,NB-1)], N = max(NA,NB)
  *     pair_mode 1: outer product, problem (ia, ib) -> index ia*NB + ib
  *     left = 0: right fixed point (x, r); left = 1: left fixed point (x, l).
- *     out (optional): eta [N] complex, vec [N][D][D] unit Frobenius norm with tr >= 0,
+ *     out (optional): eta [N] complex, vec [N][D][D] unit Frobenius norm in the gauge of the one
+ *     recorded xmps output (Time Evo.ipynb cells 22-24: LAPACK zgeev's convention, the component of
+ *     largest modulus real positive),
  *     cost [N] = -sqrt|eta| (a11, qmps/loschmidts/time_evo.py:75-116),
  *     echo [N] = -log|eta|^2, fid [N] = |eta|^2 (a8, qmps/time_evolve_tools.py:84-91),
  *     status [N]. */
 int qmps_fixed_point(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B,
                      int pair_mode, int left, void* eta, void* vec, void* cost, void* echo,
                      void* fid, int32_t* status, int dtype, void* stream);
+/* same with the phase convention of `vec` selectable: QMPS_GAUGE_ZGEEV (as above) or
+ *     QMPS_GAUGE_TRACE: tr(vec) real non-negative (traceless: largest entry real positive) -- a
+ *     Hermitian fixed point (A = B) then comes out Hermitian, which the canonical-form routines use. */
+#define QMPS_GAUGE_TRACE 0
+#define QMPS_GAUGE_ZGEEV 1
+int qmps_fixed_point_ex(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B,
+                        int pair_mode, int left, int vec_gauge, void* eta, void* vec, void* cost,
+                        void* echo, void* fid, int32_t* status, int dtype, void* stream);
 
 /* a7  merge (qmps/time_evolve_tools.py:20-23): A [NA][d1][D][D], B [NB][d2][D][D] ->
  *     M [N][d1*d2][D][D], N = max(NA,NB) (a batch of 1 broadcasts).

@@ -55,3 +55,4 @@ from .gates import *        # noqa: F401,F403
 from .costs import *        # noqa: F401,F403
 from .canonical import *    # noqa: F401,F403
 from .brickwall import *    # noqa: F401,F403
+from .stacked import *      # noqa: F401,F403

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libqmps_b200.so")
 
 C128, C64 = 0, 1
 ST_OK, ST_NOT_PD, ST_NO_CONVERGE, ST_SINGULAR = 0, 1, 2, 3
+GAUGE_TRACE, GAUGE_ZGEEV = 0, 1
 
 # gate codes (include/qmps_b200.h)
 G_RZ, G_RX, G_RY, G_H, G_CNOT, G_SWAP, G_CZ, G_XPOW, G_ZZPOW, G_XXPOW, G_YYPOW, G_X, G_Z = range(13)
@@ -42,6 +43,7 @@ SIGNATURES = {
     "qmps_env_exact": ([_i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_env_exact_host": ([_i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i], _i),
     "qmps_fixed_point": ([_i, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_fixed_point_ex": ([_i, _i, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_merge": ([_i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_ansatz": ([_gp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp], _i),
     "qmps_energy_theta": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp], _i),

@@ -119,11 +119,15 @@ def env_exact(A=None, U=None, assume_left_canonical=True, want_eta=True, want_r=
 
 
 # ---- a6 / a8 / a11 ---------------------------------------------------------------------
-def fixed_point(A, B, pair="elementwise", left=False, want_vec=True, want_costs=True, want_status=True):
+def fixed_point(A, B, pair="elementwise", left=False, want_vec=True, want_costs=True, want_status=True,
+                gauge="zgeev"):
     """Leading eigenpair of the mixed transfer matrix E_AB (``Map(A,B).right_fixed_point()``).
 
     ``pair='elementwise'``: A[NA], B[NB] broadcast (NA == NB or one of them 1).
     ``pair='outer'``: every (A[ia], B[ib]); outputs are shaped [NA, NB, ...].
+    ``gauge``: phase of the unit-norm eigenvector -- ``'zgeev'`` (largest component real positive: what
+    the recorded xmps output in the reference's ``Time Evo.ipynb`` cells 22-24 shows) or ``'trace'``
+    (tr >= 0, Hermitian-compatible).
     """
     A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
     B = _cdev(B, A.dtype, A.device)
@@ -141,8 +145,9 @@ def fixed_point(A, B, pair="elementwise", left=False, want_vec=True, want_costs=
     fid = torch.empty(shape, dtype=rd, device=dev) if want_costs else None
     st = torch.empty(shape, dtype=torch.int32, device=dev) if want_status else None
     with torch.cuda.device(dev):
-        L.check(L.load().qmps_fixed_point(d, D, NA, _p(A), NB, _p(B), int(outer), int(bool(left)), _p(eta), _p(vec),
-                                          _p(cost), _p(echo), _p(fid), _p(st), _dt(A), _stream()), "fixed_point")
+        L.check(L.load().qmps_fixed_point_ex(d, D, NA, _p(A), NB, _p(B), int(outer), int(bool(left)),
+                                             {"trace": L.GAUGE_TRACE, "zgeev": L.GAUGE_ZGEEV}[gauge], _p(eta), _p(vec),
+                                             _p(cost), _p(echo), _p(fid), _p(st), _dt(A), _stream()), "fixed_point")
     return FixedPoint(eta, vec, cost, echo, fid, st)
 
 
@@ -159,6 +164,8 @@ def merge(A, B, W=None):
         W = _cdev(W, A.dtype, A.device)
         NW = W.shape[0]
     N = max(NA, NB, NW)
+    if any(n not in (1, N) for n in (NA, NB) + ((NW,) if W is not None else ())):
+        raise ValueError(f"merge: batch sizes {NA}, {NB}, {NW} do not broadcast (each must be 1 or {N})")
     M = torch.empty((N, d1 * d2, D, D), dtype=A.dtype, device=A.device)
     with torch.cuda.device(A.device):
         L.check(L.load().qmps_merge(d1, d2, D, NA, _p(A), NB, _p(B), NW, _p(W), _p(M), _dt(A), _stream()), "merge")

@@ -108,6 +108,25 @@ inline cudaError_t malloc_async(void** ptr, size_t bytes, cudaStream_t st) {
   return cudaMallocAsync(ptr, bytes, st);
 }
 
+// stream-ordered scratch that is released on every exit path of a C-ABI entry (early CK returns included)
+struct Scratch {
+  cudaStream_t st;
+  void* ptrs[16];
+  int n;
+  explicit Scratch(cudaStream_t s) : st(s), n(0) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  template <typename U> cudaError_t get(U** p, size_t bytes) {
+    *p = nullptr;
+    if (n >= 16) return cudaErrorMemoryAllocation;
+    void* q = nullptr;
+    cudaError_t e = malloc_async(&q, bytes ? bytes : 1, st);
+    if (e == cudaSuccess) { ptrs[n++] = q; *p = (U*)q; }
+    return e;
+  }
+  ~Scratch() { for (int k = n - 1; k >= 0; --k) cudaFreeAsync(ptrs[k], st); }
+};
+
 // stream-ordered device copy of a small host array
 template <typename U> int to_device_async(const U* host, size_t count, U** dev, cudaStream_t st) {
   *dev = nullptr;

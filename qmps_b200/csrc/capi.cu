@@ -40,9 +40,10 @@ int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r
                   cudaStream_t st) {
   if (N == 0) return 0;
   const size_t DD = (size_t)D * D;
+  Scratch scratch(st);
   cx<T>* Tb = nullptr; cx<T>* Er = nullptr; T* invn = nullptr;
-  CK(malloc_async((void**)&Tb, sizeof(cx<T>) * N * d * DD, st));
-  CK(malloc_async((void**)&invn, sizeof(T) * N, st));
+  CK(scratch.get(&Tb, sizeof(cx<T>) * N * d * DD));
+  CK(scratch.get(&invn, sizeof(T) * N));
   cx<T>* r = (cx<T>*)r_io;
   const dim3 grid1((D + 31) / 32, (D + 31) / 32, (unsigned)(N * d)), grid2((D + 31) / 32, (D + 31) / 32, (unsigned)N);
   auto apply = [&](cx<T>* dst) {
@@ -56,14 +57,11 @@ int tm_power_impl(int d, int D, int64_t N, const void* A, const void* B, void* r
     scale_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, invn);
   }
   if (rayleigh) {
-    CK(malloc_async((void**)&Er, sizeof(cx<T>) * N * DD, st));
+    CK(scratch.get(&Er, sizeof(cx<T>) * N * DD));
     apply(Er);
     vdot_kernel<T><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (cx<T>*)rayleigh);
-    CK(cudaFreeAsync(Er, st));
   }
   CK(cudaGetLastError());
-  CK(cudaFreeAsync(Tb, st));
-  CK(cudaFreeAsync(invn, st));
   return 0;
 }
 
@@ -76,9 +74,10 @@ int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_
   typedef cx<double> Z;
   const size_t DD = (size_t)D * D;
   const int tx = (D + ZG_TN - 1) / ZG_TN, ty = (D + ZG_TM - 1) / ZG_TM, tiles = tx * ty;
+  Scratch scratch(st);
   Z* Tb = nullptr; Z* Er = nullptr; double* nrm = nullptr;
-  CK(malloc_async((void**)&Tb, sizeof(Z) * N * d * DD, st));
-  CK(malloc_async((void**)&nrm, sizeof(double) * N * tiles, st));
+  CK(scratch.get(&Tb, sizeof(Z) * N * d * DD));
+  CK(scratch.get(&nrm, sizeof(double) * N * tiles));
   if (int rc = allow_smem(zgemm_dmma_kernel<0>, ZG_SMEM_BYTES)) return rc;
   if (int rc = allow_smem(zgemm_dmma_kernel<1>, ZG_SMEM_BYTES)) return rc;
   Z* r = (Z*)r_io;
@@ -96,14 +95,11 @@ int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_
   for (int it = 0; it < K; ++it) apply(r, it == 0 ? nullptr : nrm, nrm);
   if (K > 0) zg_scale_kernel<<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, nrm, tiles);
   if (rayleigh) {
-    CK(malloc_async((void**)&Er, sizeof(Z) * N * DD, st));
+    CK(scratch.get(&Er, sizeof(Z) * N * DD));
     apply(Er, nullptr, nullptr);
     vdot_kernel<double><<<(unsigned)N, 256, 0, st>>>((int64_t)DD, r, Er, (Z*)rayleigh);
-    CK(cudaFreeAsync(Er, st));
   }
   CK(cudaGetLastError());
-  CK(cudaFreeAsync(Tb, st));
-  CK(cudaFreeAsync(nrm, st));
   return 0;
 }
 
@@ -204,6 +200,14 @@ int qmps_env_exact(int d, int D, int64_t N, const void* in, int in_is_full_U, in
 int qmps_fixed_point(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B, int pair_mode, int left,
                      void* eta, void* vec, void* cost, void* echo, void* fid, int32_t* status, int dtype,
                      void* stream) {
+  return qmps_fixed_point_ex(d, D, NA, A, NB, B, pair_mode, left, QMPS_GAUGE_ZGEEV, eta, vec, cost, echo, fid, status,
+                             dtype, stream);
+}
+
+int qmps_fixed_point_ex(int d, int D, int64_t NA, const void* A, int64_t NB, const void* B, int pair_mode, int left,
+                        int vec_gauge, void* eta, void* vec, void* cost, void* echo, void* fid, int32_t* status,
+                        int dtype, void* stream) {
+  if (vec_gauge != QMPS_GAUGE_TRACE && vec_gauge != QMPS_GAUGE_ZGEEV) return fail(QMPS_ERR_ARG, "fixed_point: bad vec_gauge");
   if (NA < 0 || NB < 0 || (!A && NA) || (!B && NB)) return fail(QMPS_ERR_ARG, "fixed_point: bad arguments");
   if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: D must be 1, 2, 4, 8 or 16");
   if (d < 1 || d > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: d must be 1..16");
@@ -213,6 +217,7 @@ int qmps_fixed_point(int d, int D, int64_t NA, const void* A, int64_t NB, const 
   memset(&p, 0, sizeof(p));
   p.d = d; p.D = D; p.NA = NA; p.NB = NB; p.A = A; p.B = B; p.pair_mode = pair_mode; p.left = left;
   p.N = pair_mode == 1 ? NA * NB : (NA > NB ? NA : NB);
+  p.vec_gauge = vec_gauge;
   p.eta = eta; p.vec = vec; p.cost = cost; p.echo = echo; p.fid = fid; p.status = status;
   if (dtype == QMPS_C128) return fixed_point_f64(p, (cudaStream_t)stream);
   if (dtype == QMPS_C64) return fixed_point_f32(p, (cudaStream_t)stream);
@@ -225,6 +230,8 @@ int qmps_merge(int d1, int d2, int D, int64_t NA, const void* A, int64_t NB, con
   if (d1 < 1 || d2 < 1 || D < 1 || d1 * d2 * D * D > 8192) return fail(QMPS_ERR_UNSUPPORTED, "merge: block too large");
   int64_t N = NA > NB ? NA : NB;
   if (W && NW > N) N = NW;
+  if ((NA != 1 && NA != N) || (NB != 1 && NB != N) || (W && NW != 1 && NW != N))
+    return fail(QMPS_ERR_ARG, "merge: batch sizes do not broadcast (each of NA, NB, NW must be 1 or N)");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)(N < (int64_t)sm_count() * 8 ? N : (int64_t)sm_count() * 8);
   if (dtype == QMPS_C128) {
@@ -273,7 +280,7 @@ int qmps_energy_theta(const qmps_gate_op* ops, int nops, int nq, int64_t N, int 
   GateOp* dops = nullptr;
   double* dsh = nullptr;
   if (int rc = to_device_async((const GateOp*)ops, (size_t)nops, &dops, st)) return rc;
-  if (int rc = to_device_async(shifts, (size_t)nshift, &dsh, st)) return rc;
+  if (int rc = to_device_async(shifts, (size_t)nshift, &dsh, st)) { if (dops) cudaFreeAsync(dops, st); return rc; }
   int rc = 0;
   const int D = 1 << (nq - 1);
   if (D == 2 && nops <= d2_max_ops()) {
@@ -352,16 +359,14 @@ int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* bes
   int grid = (int)((N + 255) / 256);
   if (grid > sm_count() * 4) grid = sm_count() * 4;
   if (grid < 1) grid = 1;
+  Scratch scratch(st);
   double* bc = nullptr; int64_t* bi = nullptr; unsigned int* ctr = nullptr;
-  CK(malloc_async((void**)&bc, sizeof(double) * grid, st));
-  CK(malloc_async((void**)&bi, sizeof(int64_t) * grid, st));
-  CK(malloc_async((void**)&ctr, sizeof(unsigned int), st));
+  CK(scratch.get(&bc, sizeof(double) * grid));
+  CK(scratch.get(&bi, sizeof(int64_t) * grid));
+  CK(scratch.get(&ctr, sizeof(unsigned int)));
   CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
   argmin_kernel<<<grid, 256, 0, st>>>(N, cost, index_offset, bc, bi, ctr, best_cost, best_index);
   CK(cudaGetLastError());
-  CK(cudaFreeAsync(bc, st));
-  CK(cudaFreeAsync(bi, st));
-  CK(cudaFreeAsync(ctr, st));
   return 0;
 }
 
@@ -393,17 +398,19 @@ int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_
   if (chunk > N) chunk = N;
   const int NS = 3;
   struct Slot { cudaStream_t st; char* din; char* dout; };
-  static std::mutex mu;
+  // staging slots are per device; callers on different devices do not serialise on each other
+  static std::mutex mu[64];
   static Slot slots[64][NS];
   static size_t cap_in[64] = {0}, cap_out[64] = {0};
-  std::lock_guard<std::mutex> lock(mu);
   if (device < 0 || device >= 64) return fail(QMPS_ERR_ARG, "env_exact_host: bad device");
+  std::lock_guard<std::mutex> lock(mu[device]);
   Slot* sl = slots[device];
   const size_t need_in = (size_t)chunk * in_per, need_out = (size_t)chunk * (out_per ? out_per : 1);
   if (cap_in[device] < need_in || cap_out[device] < need_out) {
+    cap_in[device] = cap_out[device] = 0;      // a failed re-allocation must not leave stale capacities / pointers
     for (int k = 0; k < NS; ++k) {
-      if (sl[k].din) cudaFree(sl[k].din);
-      if (sl[k].dout) cudaFree(sl[k].dout);
+      if (sl[k].din) { cudaFree(sl[k].din); sl[k].din = nullptr; }
+      if (sl[k].dout) { cudaFree(sl[k].dout); sl[k].dout = nullptr; }
       if (!sl[k].st) CK(cudaStreamCreateWithFlags(&sl[k].st, cudaStreamNonBlocking));
       CK(cudaMalloc((void**)&sl[k].din, need_in));
       CK(cudaMalloc((void**)&sl[k].dout, need_out));

@@ -72,7 +72,9 @@ int qmps_left_canonicalise(int d, int D, int64_t N, const void* A, void* AL, voi
   CK(malloc_async(&lvec, csz * (size_t)N * D * D, st));
   if (!eta) { CK(malloc_async(&eta_tmp, csz * (size_t)N, st)); }
   void* e = eta ? eta : eta_tmp;
-  int rc = qmps_fixed_point(d, D, N, A, N, A, 0, 1, e, lvec, nullptr, nullptr, nullptr, status, dtype, stream);
+  // l must come out Hermitian: the trace gauge (a positive multiple of a Hermitian PD matrix has tr > 0)
+  int rc = qmps_fixed_point_ex(d, D, N, A, N, A, 0, 1, QMPS_GAUGE_TRACE, e, lvec, nullptr, nullptr, nullptr, status,
+                               dtype, stream);
   if (!rc) {
     GaugeParams p;
     memset(&p, 0, sizeof(p));

@@ -82,8 +82,11 @@ QMPS_HDN int env_solve_direct(const Grp& g, const cx<T>* A, int d, int D, cx<T>*
 // |lambda|, then one inverse iteration on E - lambda for the eigenvector.
 //   adjoint = 0: right fixed point  r -> sum_s A_s r B_s^dagger         (matrix E)
 //   adjoint = 1: left fixed point   l -> sum_s A_s^dagger l B_s         (matrix E^dagger)
-// H: n x (n+1) scratch.  x[n]: eigenvector, unit norm, phase fixed so that its trace
-// is real non-negative (traceless: largest entry real positive).
+// H: n x (n+1) scratch.  x[n]: eigenvector, unit norm; gauge 0: phase fixed so that its trace
+// is real non-negative (traceless: largest entry real positive) -- the Hermitian-compatible gauge
+// the canonical-form routines need; gauge 1: LAPACK zgeev's convention (the component of largest
+// modulus real positive), which is what the one recorded xmps output shows
+// (Time Evo.ipynb cells 22-24, tests/golden/ref_notebook_outputs.json).
 template <typename T>
 QMPS_HDN void build_transfer_adj(const Grp& g, const cx<T>* A, const cx<T>* B, int d, int D,
                                  cx<T>* E, int ld, int adjoint) {
@@ -103,7 +106,7 @@ template <typename T>
 QMPS_HDN int leading_eigenpair(const Grp& g, const cx<T>* A, const cx<T>* B, int d, int D,
                                int adjoint, int want_vec, cx<T>* H, int ld, cx<T>* w, cx<T>* vv,
                                cx<T>* rc, cx<T>* rs, T* rn, cx<T>* x, int* step_row, int* done,
-                               cx<T>* lambda_out) {
+                               cx<T>* lambda_out, int gauge = 0) {
   const int n = D * D;
   build_transfer_adj<T>(g, A, B, d, D, H, ld, adjoint);
   g.sync();
@@ -143,7 +146,7 @@ QMPS_HDN int leading_eigenpair(const Grp& g, const cx<T>* A, const cx<T>* B, int
   T inv = T(1) / sqrt(nrm2);
   cx<T> ph;
   T tra = cabs(tr) * inv;
-  if (tra > T(1e-8)) ph = conj(tr) * (T(1) / cabs(tr));
+  if (gauge == 0 && tra > T(1e-8)) ph = conj(tr) * (T(1) / cabs(tr));
   else ph = conj(x[big]) * (T(1) / sqrt(bigv));
   ph = ph * inv;
   g.sync();

@@ -54,7 +54,7 @@ fp_d2_kernel(FpParams p) {
       build();
       cx<T> x[4];
       fpd2_inverse_iteration<T>(E, lam, x);
-      fpd2_fix_gauge<T>(x, 0);
+      fpd2_fix_gauge<T>(x, p.vec_gauge);
       cx<T>* o = reinterpret_cast<cx<T>*>(p.vec) + pid * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = x[i];

@@ -197,6 +197,7 @@ struct FpParams {
   int pair_mode, left;
   void* eta; void* vec; void* cost; void* echo; void* fid; int32_t* status;
   void* ws; size_t ws_stride;
+  int vec_gauge;                 // QMPS_GAUGE_TRACE (0) / QMPS_GAUGE_ZGEEV (1)
 };
 
 template <typename T, int G>
@@ -228,7 +229,7 @@ fixed_point_kernel(FpParams p) {
     const cx<T>* B = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;
     cx<T> lam;
     const int status = leading_eigenpair<T>(g, A, B, d, D, p.left, p.vec != nullptr, H, n + 1, w, vv, rc, rs,
-                                            rn, x, step_row, done, &lam);
+                                            rn, x, step_row, done, &lam, p.vec_gauge);
     if (g.lane == 0) {
       const T a2 = norm2(lam);
       if (p.eta) reinterpret_cast<cx<T>*>(p.eta)[pid] = lam;

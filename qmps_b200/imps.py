@@ -103,7 +103,7 @@ class TransferMatrix:
         res = batched.env_exact(A=A, assume_left_canonical=False, want_C=False)
         _raise_for(res.status, "TransferMatrix.eigs")
         r = _np(res.r)[0]
-        l = _np(batched.fixed_point(A, A, left=True, want_costs=False).vec)[0]
+        l = _np(batched.fixed_point(A, A, left=True, want_costs=False, gauge="trace").vec)[0]
         l = (l + l.conj().T) / 2
         l = l / np.trace(l @ r).real
         eta = complex(_np(res.eta)[0])

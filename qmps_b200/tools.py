@@ -6,6 +6,9 @@ batch of one through the C ABI into the CUDA kernels -- use ``qmps_b200.batched`
 amortise launches over many problems.  There is no CPU fallback: without the built
 library and a CUDA device these functions raise ``qmps_b200.QmpsError``.
 """
+from dataclasses import dataclass, field
+from typing import Any
+
 import numpy as np
 from numpy.linalg import LinAlgError
 from scipy.optimize import minimize, minimize_scalar
@@ -118,7 +121,7 @@ def tensor_to_unitary(A, testing=False):
         n = D * d
         passed = (np.allclose(cT(iso) @ iso, np.eye(D)) and np.allclose(U @ cT(U), np.eye(n))
                   and np.allclose(cT(U) @ U, np.eye(n)) and np.allclose(U[:, :D], iso)
-                  and np.allclose(unitary_to_tensor(U), A) if d == 2 else True)
+                  and (np.allclose(unitary_to_tensor(U), A) if d == 2 else True))
         return U, bool(passed)
     return U
 
@@ -171,83 +174,87 @@ def get_env_exact_alternative(U):
     return environment_to_unitary(res.C.cpu().numpy()[0])
 
 
-# ---- host-side drivers (keep their signatures; the cost they call is on the GPU) ------
+# ---- host-side drivers (the cost they call runs on the GPU; scipy stays on the host) -------------
+# Interface contract taken from qmps/tools.py:195-270, 459-464: the attribute names callers read
+# (`u`, `v`, `initial_guess`, `iters`, `optimized_result`, `obj_fun_values`, `settings`, `circuit`),
+# the settings keys, and the hooks subclasses override (`gate_from_params`, `update_state`,
+# `objective_function`).  The bodies are this package's own.
+_DEFAULT_SETTINGS = (("maxiter", 10000), ("verbose", True), ("method", "Nelder-Mead"), ("tol", 1e-8),
+                     ("store_values", True), ("bayesian", False))
+
+
+@dataclass
 class OptimizerCircuit:
-    def __init__(self, circuit=None, total_qubits=None, aux_qubits=None):
-        self.circuit = circuit
-        self.total_qubits = total_qubits
-        self.aux_qubits = aux_qubits
-        self.qubits = None
+    """Plain record of a circuit and its qubit bookkeeping (qmps/tools.py:195-200)."""
+    circuit: Any = None
+    total_qubits: Any = None
+    aux_qubits: Any = None
+    qubits: Any = field(default=None, init=False)
+
+
+@dataclass
+class RotosolveResult:
+    """What the rotosolve drivers return: the scipy-result fields callers read (qmps/tools.py:459-464)."""
+    history: Any
+    fun: Any
+    x: Any
+    message: str = ""
 
 
 class Optimizer:
-    """qmps/tools.py:203-270: settings dict + scipy / rotosolve dispatch."""
+    """Base class of every variational optimiser in the reference (qmps/tools.py:203-270).
+    Subclasses supply ``objective_function`` (or pass ``obj_fun``/``args``) and may override the
+    ``gate_from_params`` / ``update_state`` hooks; ``optimize`` dispatches on ``settings``."""
 
     def __init__(self, u=None, v=None, initial_guess=None, obj_fun=None, args=None):
-        self.u = u
-        self.v = v
+        self.u, self.v = u, v
         self.initial_guess = initial_guess
-        self.iters = 0
-        self.optimized_result = None
-        self.obj_fun_values = []
-        self.settings = {
-            "maxiter": 10000,
-            "verbose": True,
-            "method": "Nelder-Mead",
-            "tol": 1e-8,
-            "store_values": True,
-            "bayesian": False,
-        }
+        self.obj_fun, self.args = obj_fun, args
+        self.settings = dict(_DEFAULT_SETTINGS)
         self.is_verbose = self.settings["verbose"]
-        self.obj_fun = obj_fun
-        self.args = args
         self.circuit = OptimizerCircuit()
+        self.iters, self.obj_fun_values, self.optimized_result = 0, [], None
 
+    # -- hooks ------------------------------------------------------------------------------
+    def gate_from_params(self, params):
+        return None
+
+    def update_state(self):
+        return None
+
+    def objective_function(self, params):
+        if self.obj_fun is None:
+            return None
+        return self.obj_fun(params, *(self.args or ()))
+
+    # -- driver -------------------------------------------------------------------------------
     def change_settings(self, new_settings):
         return self.settings.update(new_settings)
 
-    def gate_from_params(self, params):
-        pass
-
-    def update_state(self):
-        pass
-
     def callback_store_values(self, xk):
-        val = self.objective_function(xk)
-        self.obj_fun_values.append(val)
+        """scipy callback: record (and, when verbose, print ``iteration:value``) the cost at ``xk``."""
+        value = self.objective_function(xk)
+        self.obj_fun_values.append(value)
         if self.settings["verbose"]:
-            print(f"{self.iters}:{val}")
+            print("%d:%s" % (self.iters, value))
         self.iters += 1
 
-    def objective_function(self, params):
-        if self.obj_fun is not None:
-            return self.obj_fun(params, *(self.args or ()))
+    def _run_minimiser(self):
+        cfg = self.settings
+        if cfg["bayesian"]:
+            raise NotImplementedError("bayesian optimisation needs skopt, which the reference has commented out")
+        if cfg["method"] == "Rotosolve":
+            return double_rotosolve(self.objective_function, self.initial_guess, cfg["maxiter"], cfg["verbose"])
+        return minimize(self.objective_function, self.initial_guess, method=cfg["method"], tol=cfg["tol"],
+                        callback=self.callback_store_values if cfg["store_values"] else None,
+                        options={"maxiter": cfg["maxiter"], "disp": cfg["verbose"]})
 
     def optimize(self):
-        s = self.settings
-        options = {"maxiter": s["maxiter"], "disp": s["verbose"]}
-        if s["bayesian"]:
-            raise NotImplementedError("bayesian optimisation (skopt) is commented out in the reference too")
-        if s["method"] == "Rotosolve":
-            self.optimized_result = double_rotosolve(self.objective_function, self.initial_guess,
-                                                     options["maxiter"], options["disp"])
-        else:
-            self.optimized_result = minimize(fun=self.objective_function, x0=self.initial_guess,
-                                             method=s["method"], tol=s["tol"], options=options,
-                                             callback=self.callback_store_values if s["store_values"] else None)
+        self.optimized_result = res = self._run_minimiser()
         self.update_state()
-        if s["verbose"]:
-            print(f"Reason for termination is {self.optimized_result.message} "
-                  f"\nObjective Function Value is {self.optimized_result.fun}")
-        return self.optimized_result
-
-
-class RotosolveResult(object):
-    def __init__(self, history, fun, x, message):
-        self.history = history
-        self.fun = fun
-        self.x = x
-        self.message = message
+        if self.is_verbose:
+            print("Reason for termination is %s \nObjective Function Value is %s" % (res.message, res.fun))
+        return res
 
 
 def double_rotosolve(ϵ, initial_parameters, N_iters=100, disp=True):

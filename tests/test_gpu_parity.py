@@ -155,10 +155,16 @@ def test_fixed_point_vs_oracle(env, D, count, left):
     t, B, O = env["torch"], env["B"], env["O"]
     A, Bt = tensors(D, count, 300 + D, O), tensors(D, count, 900 + D, O)
     fp = B.fixed_point(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), left=left)
+    vec_tr = B.fixed_point(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), left=left, gauge="trace").vec.cpu().numpy()
     assert int(fp.status.abs().sum()) == 0
     eta, vec = fp.eta.cpu().numpy(), fp.vec.cpu().numpy()
     for k in range(count):
         x0, v0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])
+        # default gauge = zgeev's (the notebook-recorded xmps convention): largest entry real positive
+        big = vec[k].reshape(-1)[np.argmax(np.abs(vec[k]))]
+        assert abs(big.imag) < 1e-12 and big.real > 0
+        assert abs(np.trace(vec_tr[k]).imag) < 1e-12 and np.trace(vec_tr[k]).real >= 0
+        assert abs(abs(np.vdot(vec_tr[k], vec[k])) - 1) < 1e-10        # same ray, different phase
         E = O.transfer_matrix(A[k], Bt[k])
         Em = E.conj().T if left else E
         w = np.sort(np.abs(np.linalg.eigvals(E)))[::-1]

@@ -258,7 +258,7 @@ def test_emu_fp_d2_register_eigenvalue_path(emu, left):
             gap = max(np.abs(w - eta[k])[np.argsort(np.abs(w - eta[k]))[1]], 1e-3)
             assert abs(np.linalg.norm(v) - 1) < 1e-12
             assert np.abs(Em @ v - eta[k] * v).max() < 1e-11 / gap
-            x0, v0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], B[k])
+            x0, v0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], B[k], gauge="trace")
             if abs(eta[k] - x0) < 1e-9:                    # same eigenvalue picked: same gauge-fixed vector
                 assert np.abs(vec[k] - v0).max() < 1e-9 / gap
 

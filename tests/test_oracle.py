@@ -281,3 +281,79 @@ def test_get_overlap_exact_matches_reference_function(golden):
             f, r = O.get_overlap_exact(g["p0"][a], g["ps"][b])
             assert abs(f - g["overlap"][a, b]) < 1e-12
     assert abs(g["overlap"][0, 0] - 1) < 1e-12
+
+
+# ---------------------------------------------------------------- xmps outputs recorded in the reference's notebooks
+def _notebook_cells():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_notebook_outputs.json")
+    with open(path) as f:
+        g = json.load(f)["cells"]
+    mat = lambda c: (np.array(c["re"]) + 1j * np.array(c["im"])).reshape(c["shape"])
+    return g, mat
+
+
+def test_notebook_recorded_xmps_fixed_points_pin_norm_and_gauge():
+    """`Time Evo.ipynb` cells 22-24 print `Map(A,B).left_fixed_point()[1]` (oracle/make_golden_notebooks.py):
+    unit Frobenius norm, zgeev's phase convention (largest entry real positive) -- NOT tr >= 0 -- and the
+    same vector for the merged two-site map.  `scripts/opt.ipynb` cell 11 is another xmps version
+    (array-valued eigenvalue, norm 1.2): recorded, pins only the `x[0]` indexing of time_evo.py:113."""
+    from oracle.tensors import _fix_phase_zgeev, _fix_phase_unit
+    g, mat = _notebook_cells()
+    m23, m24 = mat(g["time_evo_23_left_fixed_point"]), mat(g["time_evo_24_left_fixed_point_merged"])
+    assert abs(np.linalg.norm(m23) - 1) < 1e-8 and abs(np.linalg.norm(m24) - 1) < 1e-8
+    assert np.abs(_fix_phase_zgeev(m23) - m23).max() < 1e-8           # the oracle's default gauge leaves it alone
+    assert np.abs(_fix_phase_unit(m23) - m23).max() > 0.1             # the tr >= 0 gauge would rotate it
+    assert np.abs(m23 - m24).max() < 1e-8
+    assert g["opt_11_left_fixed_point"]["eta_shape"] == [1]
+    assert abs(np.linalg.norm(mat(g["opt_11_left_fixed_point"])) - 1) > 0.2
+
+
+def test_merged_map_has_same_fixed_point_as_single_site_map():
+    """The identity cells 23/24 of `Time Evo.ipynb` exhibit, on seeded inputs built as the cell builds
+    them (A left-canonical, B = exp(-i Z dt) . A on the physical index, dt = 0.01): Map(merge(A,A),
+    merge(B,B)) has the fixed points of Map(A,B) and the squared eigenvalue."""
+    from scipy.linalg import expm
+    Z = np.diag([1.0, -1.0])
+    for seed in range(6):
+        A = O.unitary_to_tensor(unitary_group.rvs(4, random_state=40 + seed))
+        Bt = np.tensordot(expm(-1j * Z * 0.01), A, [1, 0])
+        for fp in (O.left_fixed_point, O.right_fixed_point):
+            x, v = fp(A, Bt)
+            x2, v2 = fp(O.merge(A, A), O.merge(Bt, Bt))
+            assert abs(x2 - x * x) < 1e-12 and np.abs(v - v2).max() < 1e-10
+            assert abs(np.linalg.norm(v) - 1) < 1e-12
+            big = v.reshape(-1)[np.argmax(np.abs(v))]
+            assert abs(big.imag) < 1e-14 and big.real > 0
+
+
+# ---------------------------------------------------------------- stacked forms == per-call oracle
+def test_stacked_forms_equal_per_call_oracle():
+    """oracle/stacked.py (the full-size checker and the B2 'vectorised CPU' baseline) against the
+    per-call restatement, function by function."""
+    U = O.haar_unitaries(4, 64, 1)
+    assert np.array_equal(U, unitary_group.rvs(4, size=64, random_state=1)) and np.allclose(U[3] @ U[3].conj().T, np.eye(4))
+    A = O.tensors_of_unitaries(U)
+    for D in (2, 4):
+        if D == 4:
+            U = O.haar_unitaries(8, 16, 2)
+            A = O.tensors_of_unitaries(U)
+        assert all(np.array_equal(A[k], O.unitary_to_tensor(U[k])) for k in range(len(U)))
+        eta, r = O.stacked_env_exact(A)
+        C, v0 = O.stacked_cholesky_env(r)
+        H = O.tfim_matrix(0.7)
+        e = O.stacked_energy_transfer(A, H)
+        for k in range(len(U)):
+            e0, r0, C0, v00 = O.env_exact_parts(A[k])
+            assert abs(eta[k] - e0) < 1e-12 and np.abs(r[k] - r0).max() < 1e-11
+            assert np.abs(C[k] - C0).max() < 1e-10 and np.abs(v0[k] - v00).max() < 1e-10
+            assert abs(e[k] - O.energy_transfer(A[k], H)) < 1e-11
+        W = np.stack([O.tfim_evolution_gate(0.2, 0.05 * k) for k in range(3)])
+        cost, echo = O.stacked_loschmidt_costs(A[0], A[1:6], W)
+        for p in range(5):
+            for k in range(3):
+                assert abs(cost[p, k] - O.loschmidt_cost(A[0], A[1 + p], W[k])) < 1e-12
+        assert np.abs(echo + 4 * np.log(-cost)).max() < 1e-12
+    got = O.parallel_map_chunks(O.stacked_env_exact, [A], nproc=2, chunk=5)
+    assert np.abs(np.concatenate([g[1] for g in got]) - r).max() == 0
