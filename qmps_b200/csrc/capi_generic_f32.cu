@@ -2,7 +2,8 @@
 // the two precisions compile in parallel).
 #include "api_common.cuh"
 #include "launch_envreal.cuh"
-#include "kernels_fp16.cuh"
+#include "kernels_fp16x8.cuh"
+#include "kernels_fp16s.cuh"
 #include "kernels_fpd2.cuh"
 
 using namespace qmps;
@@ -49,11 +50,11 @@ template <int MODE> int dispatch_env(const EnvParams& p, cudaStream_t st) {
 }
 
 // D = 4 eigenvalue-only fast path (kernels_fp16.cuh): half a warp per problem
-int launch_fp16(FpParams p, cudaStream_t st) {
+template <int MINB> int launch_fp16_v(FpParams p, cudaStream_t st) {
   const Fp16Layout<REAL> L = fp16_layout<REAL>(p.d);
   const int block = 128, gpc = block / 16;
   const size_t smem = L.total * gpc;
-  auto kern = fp16_kernel<REAL>;
+  auto kern = fp16_kernel<REAL, MINB>;
   if (int rc = allow_smem(kern, smem)) return rc;
   int grid = 1;
   if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
@@ -61,6 +62,60 @@ int launch_fp16(FpParams p, cudaStream_t st) {
   kern<<<grid, block, smem, st>>>(p);
   CK(cudaGetLastError());
   return 0;
+}
+// quarter-warp form (kernels_fp16x8.cuh): eight lanes per problem, CTAs of 64 threads
+template <int MINB> int launch_fp16x8_v(FpParams p, cudaStream_t st) {
+  const Fp16Layout<REAL> L = fp16_layout<REAL>(p.d);
+  const int block = 64, gpc = block / 8;
+  const size_t smem = L.total * gpc;
+  auto kern = fp16x8_kernel<REAL, MINB>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+// shared-resident form (kernels_fp16s.cuh): half a warp per problem, matrix in a swizzled shared tile
+int launch_fp16s(FpParams p, cudaStream_t st) {
+  const Fp16sLayout<REAL> L = fp16s_layout<REAL>();
+  const int block = 128, gpc = block / 16;
+  const size_t smem = L.total * gpc;
+  auto kern = fp16s_kernel<REAL>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+int launch_fp16s8(FpParams p, cudaStream_t st) {
+  const Fp16sLayout<REAL> L = fp16s_layout<REAL>();
+  const int block = 64, gpc = block / 8;
+  const size_t smem = L.total * gpc;
+  auto kern = fp16s8_kernel<REAL>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, block, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+// option fp16_fast: 6 = shared-resident form, 7 = its quarter-warp variant; 1 / 2 = half-warp form with the register budget of 3 / 4 CTAs per SM;
+// 3 / 4 / 5 = quarter-warp form with the register budget of 4 / 5 / 6 CTAs (of 64 threads) per SM
+int launch_fp16(const FpParams& p, cudaStream_t st) {
+  switch (option_get(OPT_FP16_FAST)) {
+    case 2: return launch_fp16_v<4>(p, st);
+    case 3: return launch_fp16x8_v<4>(p, st);
+    case 4: return launch_fp16x8_v<5>(p, st);
+    case 5: return launch_fp16x8_v<6>(p, st);
+    case 6: return launch_fp16s(p, st);
+    case 7: return launch_fp16s8(p, st);
+    default: return launch_fp16_v<3>(p, st);
+  }
 }
 
 // D = 2 eigenvalue-only path (kernels_fpd2.cuh): one thread per problem, registers only

@@ -14,6 +14,12 @@
 //   * deflation is detected by all sub-diagonal entries at once (one ballot);
 //   * the two problems of a warp execute one converged instruction stream: every decision
 //     that steers control flow is made warp-uniform, per-problem differences are predicated.
+// Code size is what decides this kernel (round-1 version: four fully unrolled sweep variants and an
+// unrolled Hessenberg reduction, 63 % of the stall samples were instruction-cache misses,
+// profiles/ncu_fp16_r02a.txt): there is ONE sweep body whose unrolled steps are skipped by
+// warp-uniform branches outside the union of the two active windows, and the Hessenberg loop is a
+// real loop (the reflector is zero above the current column, so every step runs the same
+// 16-row body).
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels_generic.cuh"
@@ -29,12 +35,15 @@ template <typename T> struct Fp16Layout { size_t S, rot, vbuf, ubuf, A, B, total
 template <typename T> QMPS_HD Fp16Layout<T> fp16_layout(int d) {
   Fp16Layout<T> L;
   Bump b;
-  L.S = b.take(sizeof(cx<T>) * F16_N * F16_LD);
-  L.rot = b.take(sizeof(cx<T>) * 2 * F16_N);
+  // A / B staging is dead once the columns of E are built and shares the tile S when it fits;
+  // the rotation table of the QR phase shares the reflector buffers of the Hessenberg phase.
+  const size_t s_bytes = sizeof(cx<T>) * F16_N * F16_LD, ab_bytes = sizeof(cx<T>) * (size_t)d * F16_N;
+  L.S = b.take(s_bytes);
   L.vbuf = b.take(sizeof(cx<T>) * 2 * F16_N);
+  L.rot = L.vbuf;
   L.ubuf = b.take(sizeof(cx<T>) * F16_N);
-  L.A = b.take(sizeof(cx<T>) * (size_t)d * F16_N);
-  L.B = b.take(sizeof(cx<T>) * (size_t)d * F16_N);
+  if (2 * ab_bytes <= s_bytes) { L.A = L.S; L.B = L.S + ab_bytes; }
+  else { L.A = b.take(ab_bytes); L.B = b.take(ab_bytes); }
   L.total = (b.off + 127) & ~size_t(127);
   return L;
 }
@@ -51,64 +60,72 @@ template <typename T> __device__ __forceinline__ cx<T> shfl16(cx<T> v, int src) 
 }
 
 // One explicit shifted-QR sweep on the window [l, en] of each half-warp's matrix.
-// ENT: compile-time bound on en for BOTH problems of the warp (rotations i = 1 .. ENT).
-template <typename T, int ENT>
-__device__ __forceinline__ void fp16_sweep(cx<T> (&h)[F16_N], int ln, int l, int en, cx<T> sigma,
-                                           cx<T>* S, cx<T>* rot) {
-  // H - sigma on the window's diagonal; the negligible entry H[l][l-1] becomes an exact zero
+// In: the row-major copy S of the matrix.  Out: S again (what the deflation test and the next shift read).
+// The registers h[] are live inside the sweep only.  Steps i <= lo or i > hi are skipped by warp-uniform
+// branches (lo = min l, hi = max en over the two problems of the warp).  Everything that addresses the
+// matrix by a lane-dependent index (the diagonal shift, the exact zero at H[l][l-1]) is done on the
+// shared copy -- in registers it would cost a compare-and-select per row.
+template <typename T>
+__device__ __forceinline__ void fp16_sweep(int ln, int l, int en, int lo, int hi, cx<T> sigma, cx<T>* S,
+                                           cx<T>* rot) {
+  const bool in_win = (ln >= l) && (ln <= en);
+  if (in_win) S[ln * F16_LD + ln] = S[ln * F16_LD + ln] - sigma;          // H - sigma on the window's diagonal
+  if (l >= 1 && ln == l - 1) S[l * F16_LD + (l - 1)] = mk<T>(0, 0);        // the negligible entry becomes exact
+  __syncwarp();
+  cx<T> h[F16_N];
 #pragma unroll
-  for (int i = 0; i < F16_N; ++i) {
-    if (i == ln && i >= l && i <= en) h[i] = h[i] - sigma;
-    if (i >= 1 && i == l && ln == l - 1) h[i] = mk<T>(0, 0);
-  }
+  for (int i = 0; i < F16_N; ++i)
+    if (i <= hi) h[i] = S[i * F16_LD + ln];                                 // my column
+  __syncwarp();
   // left phase: R = G_en ... G_{l+1} (H - sigma), column-local
 #pragma unroll
-  for (int i = 1; i <= ENT; ++i) {
-    const bool act = (i > l) && (i <= en);
-    const cx<T> f = shfl16(h[i - 1], i - 1), g = shfl16(h[i], i - 1);
-    const T nr2 = norm2(f) + norm2(g);
-    cx<T> c = mk<T>(1, 0), s = mk<T>(0, 0);
-    T nr = T(0);
-    if (act && nr2 > T(0)) {
-      const T inr = rsqrt_t<T>(nr2);
-      c = f * inr; s = g * inr; nr = nr2 * inr;
+  for (int i = 1; i < F16_N; ++i) {
+    if (i > lo && i <= hi) {
+      const bool act = (i > l) && (i <= en);
+      const cx<T> f = shfl16(h[i - 1], i - 1), g = shfl16(h[i], i - 1);
+      const T nr2 = norm2(f) + norm2(g);
+      cx<T> c = mk<T>(1, 0), s = mk<T>(0, 0);
+      T nr = T(0);
+      if (act && nr2 > T(0)) {
+        const T inr = rsqrt_t<T>(nr2);
+        c = f * inr; s = g * inr; nr = nr2 * inr;
+      }
+      if (ln == 0) { rot[2 * i] = c; rot[2 * i + 1] = s; }
+      const cx<T> p = h[i - 1], q = h[i];
+      cx<T> top = conj(c) * p; cmad(top, conj(s), q);
+      cx<T> bot = c * q; cmsub(bot, s, p);
+      h[i - 1] = top; h[i] = bot;
+      if (act && ln == i - 1) { h[i - 1] = mk<T>(nr, 0); h[i] = mk<T>(0, 0); }
     }
-    if (ln == 0) { rot[2 * i] = c; rot[2 * i + 1] = s; }
-    const cx<T> p = h[i - 1], q = h[i];
-    cx<T> top = conj(c) * p; cmad(top, conj(s), q);
-    cx<T> bot = c * q; cmsub(bot, s, p);
-    h[i - 1] = top; h[i] = bot;
-    if (act && ln == i - 1) { h[i - 1] = mk<T>(nr, 0); h[i] = mk<T>(0, 0); }
   }
-  // transpose: columns -> rows
+  // transpose: columns -> rows (rows / columns beyond hi are never read again)
 #pragma unroll
-  for (int i = 0; i < F16_N; ++i) S[i * F16_LD + ln] = h[i];
+  for (int i = 0; i < F16_N; ++i)
+    if (i <= hi) S[i * F16_LD + ln] = h[i];
   __syncwarp();
-#pragma unroll
-  for (int j = 0; j < F16_N; ++j) h[j] = S[ln * F16_LD + j];
-  // right phase: H' = R G_{l+1}^H ... G_en^H + sigma, row-local (rot[] is uniform per problem)
-#pragma unroll
-  for (int j = 1; j <= ENT; ++j) {
-    const cx<T> c = rot[2 * j], s = rot[2 * j + 1];
-    const cx<T> xx = h[j - 1], yy = h[j];
-    cx<T> a = xx * c; cmad(a, yy, s);
-    cx<T> b = yy * conj(c); cmsub(b, xx, conj(s));
-    h[j - 1] = a; h[j] = b;
-  }
 #pragma unroll
   for (int j = 0; j < F16_N; ++j)
-    if (j == ln && j >= l && j <= en) h[j] = h[j] + sigma;
-  __syncwarp();
-  // rows -> shared (the row-major copy the deflation test and the shift read) -> columns
+    if (j <= hi) h[j] = S[ln * F16_LD + j];
+  // right phase: H' = R G_{l+1}^H ... G_en^H + sigma, row-local (rot[] is uniform per problem)
 #pragma unroll
-  for (int j = 0; j < F16_N; ++j) S[ln * F16_LD + j] = h[j];
-  __syncwarp();
+  for (int j = 1; j < F16_N; ++j) {
+    if (j > lo && j <= hi) {
+      const cx<T> c = rot[2 * j], s = rot[2 * j + 1];
+      const cx<T> xx = h[j - 1], yy = h[j];
+      cx<T> a = xx * c; cmad(a, yy, s);
+      cx<T> b = yy * conj(c); cmsub(b, xx, conj(s));
+      h[j - 1] = a; h[j] = b;
+    }
+  }
+  // my row back to the shared copy (same thread reads and writes row ln here), then + sigma on the diagonal
 #pragma unroll
-  for (int i = 0; i < F16_N; ++i) h[i] = S[i * F16_LD + ln];
+  for (int j = 0; j < F16_N; ++j)
+    if (j <= hi) S[ln * F16_LD + j] = h[j];
+  if (in_win) S[ln * F16_LD + ln] = S[ln * F16_LD + ln] + sigma;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(128, 3)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 fp16_kernel(FpParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = p.d;
@@ -143,33 +160,37 @@ fp16_kernel(FpParams p) {
     cx<T> h[F16_N];
 #pragma unroll
     for (int r = 0; r < F16_N; ++r) h[r] = mk<T>(0, 0);
+    // right: E[(i,k),(j,l)] = sum_s A[s,i,j] conj(B[s,k,l]), my column (j,l) = (jj,ll);
+    // left:  E^dagger[(i,k),(j,l)] = conj(A[s,j,i] conj(B[s,l,k])): same products, transposed reads, conjugated
     const int jj = ln >> 2, ll = ln & 3;
+    const int sa = p.left ? 1 : 4, oa = p.left ? jj * 4 : jj, ob = p.left ? ll * 4 : ll;
+#pragma unroll 1
     for (int s = 0; s < d; ++s) {
       cx<T> a[4], b[4];
-      if (!p.left) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = As[s * 16 + i * 4 + jj]; b[i] = Bs[s * 16 + i * 4 + ll]; }
+      for (int i = 0; i < 4; ++i) { a[i] = As[s * 16 + i * sa + oa]; b[i] = Bs[s * 16 + i * sa + ob]; }
 #pragma unroll
-        for (int r = 0; r < F16_N; ++r) cmad_c(h[r], a[r >> 2], b[r & 3]);      // A[s,i,j] conj(B[s,k,l])
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = As[s * 16 + jj * 4 + i]; b[i] = Bs[s * 16 + ll * 4 + i]; }
-#pragma unroll
-        for (int r = 0; r < F16_N; ++r) cmad_c(h[r], b[r & 3], a[r >> 2]);      // conj(A[s,j,i]) B[s,l,k]
-      }
+      for (int r = 0; r < F16_N; ++r) cmad_c(h[r], a[r >> 2], b[r & 3]);
     }
-    // ---- Householder reduction to Hessenberg form, column-local left updates
+    if (p.left) {
 #pragma unroll
+      for (int r = 0; r < F16_N; ++r) h[r].im = -h[r].im;
+    }
+    __syncwarp();                                          // A / B staging may share the tile S
+    // ---- Householder reduction to Hessenberg form, column-local left updates.
+    // A real loop: the reflector v has v[i] = 0 for i <= k, so every step runs the same 16-row body.
+#pragma unroll 1
     for (int k = 0; k + 2 < F16_N; ++k) {
       if (ln == k) {
 #pragma unroll
-        for (int i = k + 1; i < F16_N; ++i) vbuf[i] = h[i];
+        for (int i = 0; i < F16_N; ++i) vbuf[i] = h[i];
       }
       __syncwarp();
       const cx<T> alpha = vbuf[k + 1];
-      T xn2 = T(0);
+      // |x|^2 of the entries below the sub-diagonal: one entry per lane, butterfly sum over the half-warp
+      T xn2 = (ln > k + 1) ? norm2(vbuf[ln]) : T(0);
 #pragma unroll
-      for (int i = k + 2; i < F16_N; ++i) xn2 += norm2(vbuf[i]);
+      for (int m = 8; m >= 1; m >>= 1) xn2 += __shfl_xor_sync(0xffffffffu, xn2, m, 16);
       const bool skip = (xn2 == T(0)) && (alpha.im == T(0));
       T beta = sqrt(norm2(alpha) + xn2);
       if (alpha.re > T(0)) beta = -beta;
@@ -188,14 +209,20 @@ fp16_kernel(FpParams p) {
       // left:  H <- (1 - conj(tau) v v^H) H   on my column
       cx<T> w = mk<T>(0, 0);
 #pragma unroll
-      for (int i = k + 1; i < F16_N; ++i) cmad(w, conj(vbuf[16 + i]), h[i]);
+      for (int i = 1; i < F16_N; ++i) cmad(w, conj(vbuf[16 + i]), h[i]);
       w = w * conj(tau);
 #pragma unroll
-      for (int i = k + 1; i < F16_N; ++i) cmsub(h[i], vbuf[16 + i], w);
-      if (!skip && ln == k) {
-        h[k + 1] = mk<T>(beta, 0);
+      for (int i = 1; i < F16_N; ++i) cmsub(h[i], vbuf[16 + i], w);
+      {
+        // column k below the diagonal becomes (beta, 0, ..., 0): selects on every row (a store under
+        // "i == k + 1" would be turned into a dynamically indexed store and push h[] to local memory)
+        const bool fix = !skip && ln == k;
 #pragma unroll
-        for (int i = k + 2; i < F16_N; ++i) h[i] = mk<T>(0, 0);
+        for (int i = 1; i < F16_N; ++i) {
+          const bool sub = fix && (i == k + 1), below = fix && (i > k + 1);
+          h[i].re = sub ? beta : (below ? T(0) : h[i].re);
+          h[i].im = (sub || below) ? T(0) : h[i].im;
+        }
       }
       // right: H <- H (1 - tau v v^H):  u = H v (row sums through the shared tile), H -= tau u v^H
 #pragma unroll
@@ -203,7 +230,7 @@ fp16_kernel(FpParams p) {
       __syncwarp();
       cx<T> u = mk<T>(0, 0);
 #pragma unroll
-      for (int j = 0; j < F16_N; ++j) u = u + S[ln * F16_LD + j];
+      for (int j = 1; j < F16_N; ++j) u = u + S[ln * F16_LD + j];
       ubuf[ln] = u * tau;
       __syncwarp();
       const cx<T> cvj = conj(vj);
@@ -220,6 +247,7 @@ fp16_kernel(FpParams p) {
     int en = F16_N - 1, its = 0, fail = 0, sweeps = 0;
     T best2 = T(-1);
     cx<T> best = mk<T>(0, 0);
+#pragma unroll 1
     for (;;) {
       // negligible sub-diagonal entries, all at once
       bool neg = false;
@@ -243,7 +271,6 @@ fp16_kernel(FpParams p) {
         } else break;
       }
       if (__all_sync(0xffffffffu, en < 0)) break;
-      const int en_max = max(en, __shfl_xor_sync(0xffffffffu, en, 16));
       // shift (Wilkinson; exceptional every 10 stalled sweeps) -- idle problem: l = en = 0, sigma = 0
       cx<T> sigma = mk<T>(0, 0);
       int lw = 0, enw = 0;
@@ -265,11 +292,13 @@ fp16_kernel(FpParams p) {
           }
         }
       }
+      // union of the two active windows of this warp (an idle problem has the empty window [15, 0])
+      const int lo_mine = (en >= 1) ? lw : F16_N - 1, hi_mine = (en >= 1) ? enw : 0;
+      // redux.sync results live in uniform registers: the window branches below are provably warp-uniform
+      const int lo = __reduce_min_sync(0xffffffffu, lo_mine);
+      const int hi = __reduce_max_sync(0xffffffffu, hi_mine);
       __syncwarp();
-      if (en_max > 11) fp16_sweep<T, 15>(h, ln, lw, enw, sigma, S, rot);
-      else if (en_max > 7) fp16_sweep<T, 11>(h, ln, lw, enw, sigma, S, rot);
-      else if (en_max > 3) fp16_sweep<T, 7>(h, ln, lw, enw, sigma, S, rot);
-      else fp16_sweep<T, 3>(h, ln, lw, enw, sigma, S, rot);
+      fp16_sweep<T>(ln, lw, enw, lo, hi, sigma, S, rot);
       __syncwarp();
       ++its;
       if (en >= 1) ++sweeps;
