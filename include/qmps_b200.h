@@ -119,6 +119,7 @@ int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_
  *     A [NA][d][D][D], B [NB][d][D][D].
  *     pair_mode 0: problem i uses A[min(i,NA-1)] , B[min(i,NB-1)], N = max(NA,NB)
  *     pair_mode 1: outer product, problem (ia, ib) -> index ia*NB + ib
+ *     pair_mode 2: outer product, B-major output: problem (ia, ib) -> index ib*NA + ia
  *     left = 0: right fixed point (x, r); left = 1: left fixed point (x, l).
  *     out (optional): eta [N] complex, vec [N][D][D] unit Frobenius norm in the gauge of the one
  *     recorded xmps output (Time Evo.ipynb cells 22-24: LAPACK zgeev's convention, the component of
@@ -283,6 +284,46 @@ int qmps_bw_evolve_cost(int64_t N, int64_t NK, const void* U1, const void* U2, i
  *     step is one NCCL all-gather of 16 bytes per rank (qmps_b200/dist.py). */
 int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* best_cost,
                 int64_t* best_index, void* stream);
+
+
+/* ---- single-call pipelines (SURVEY 8(b) proposal) ---------------------------------------------------- */
+
+/* a11 in one call (qmps/loschmidts/time_evo.py:75-116 = scripts/loschmidt.py:209-239 for a whole grid):
+ *     for NP parameter vectors theta [NP][P] of the gate program and NT two-site gates W [NT][4][4] applied to
+ *     the state tensor A0 [2][D][D] (D = 2^(nq-1)):  eta_2 = leading eigenvalue of
+ *     Map(W_k . merge(A0,A0), merge(B_p,B_p)), cost [NP][NT] = -sqrt|eta_2|, echo [NP][NT] = -log|eta_2|^2,
+ *     eta [NP][NT] complex, status [NP][NT]; any output may be NULL.  Four launches on `stream`. */
+int qmps_loschmidt_batched(const qmps_gate_op* ops, int nops, int nq, int64_t NP, int P, const double* theta,
+                           const void* A0, int64_t NT, const void* W, void* cost, void* echo, void* eta,
+                           int32_t* status, int dtype, void* stream);
+/* same with HOST buffers (pageable or pinned): 8 P bytes in and 8 NT bytes out per parameter vector */
+int qmps_loschmidt_batched_host(const qmps_gate_op* ops, int nops, int nq, int64_t NP, int P, const double* theta,
+                                const void* A0, int64_t NT, const void* W, void* cost, void* echo, void* eta,
+                                int32_t* status, int dtype, int device);
+
+/* a9 / a12 with HOST buffers: theta [N][P] in, energy [N][max(nshift,1)] (+ status) out
+ *     (qmps/ground_state.py:150-168, 251-266; shifts as qmps/rotosolve.py:175) */
+int qmps_energy_theta_host(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, const double* theta,
+                           const void* hmat, int coord, const double* shifts, int nshift, void* energy,
+                           int32_t* status, int dtype, int device);
+
+/* a12 whole coordinate sweeps on the device: for each of n_sweeps sweeps and each coordinate i the fused
+ *     shift fan-out + energy launch and the closed-form update (two_frequency = 0: qmps/rotosolve.py:154-181,
+ *     3 shifts; 1: qmps/tools.py:422-457, 6 shifts).  theta [N][P] (DEVICE) is updated in place; energy [N]
+ *     (optional, DEVICE) receives the cost after the last sweep.  No host round trip. */
+int qmps_rotosolve_sweep(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, double* theta, const void* hmat,
+                         int n_sweeps, int two_frequency, void* energy, int dtype, void* stream);
+
+/* (e)  the final cost reduction across ranks: local argmin, one ncclAllGather of 16 bytes per
+ *     rank and a final pass, all on `stream`; best_cost [1] / best_index [1] are DEVICE scalars, identical on
+ *     every rank (ties: smallest global index; an empty shard contributes nothing).  `comm` is an ncclComm_t --
+ *     the caller's own (qmps_nccl_comm_create) or an existing one, e.g. torch's ProcessGroupNCCL communicator;
+ *     NULL means a single rank.  NCCL is bound at run time to the libnccl.so.2 already loaded in the process. */
+int qmps_argmin_allreduce(void* comm, int64_t N, const double* cost, int64_t index_offset, double* best_cost,
+                          int64_t* best_index, void* stream);
+int qmps_nccl_unique_id(void* id128);                                        /* ncclGetUniqueId (128 bytes), rank 0 */
+int qmps_nccl_comm_create(const void* id128, int world, int rank, void** comm);   /* ncclCommInitRank on the current device */
+int qmps_nccl_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

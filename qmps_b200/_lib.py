@@ -44,6 +44,14 @@ SIGNATURES = {
     "qmps_env_exact_host": ([_i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i], _i),
     "qmps_fixed_point": ([_i, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_fixed_point_ex": ([_i, _i, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_loschmidt_batched": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_loschmidt_batched_host": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
+    "qmps_energy_theta_host": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i], _i),
+    "qmps_rotosolve_sweep": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
+    "qmps_argmin_allreduce": ([_vp, _i64, _vp, _i64, _vp, _vp, _vp], _i),
+    "qmps_nccl_unique_id": ([_vp], _i),
+    "qmps_nccl_comm_create": ([_vp, _i, _i, _vp], _i),
+    "qmps_nccl_comm_destroy": ([_vp], _i),
     "qmps_merge": ([_i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_ansatz": ([_gp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp], _i),
     "qmps_energy_theta": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp], _i),

@@ -264,36 +264,85 @@ def rotosolve_fit(costs, theta=None, coord=None):
 
 
 def rotosolve_sweeps(program, theta, H, n_sweeps=1, double=False, dtype=torch.complex128):
-    """Whole coordinate sweeps on the device for a batch of parameter vectors: for each
-    coordinate, one fused (shift fan-out + energy) launch and one closed-form update
-    launch -- no host round trip.  ``theta`` is updated in place.
+    """Whole coordinate sweeps on the device for a batch of parameter vectors, ONE C-ABI call
+    (``qmps_rotosolve_sweep``): for each coordinate a fused (shift fan-out + energy) launch and a
+    closed-form update launch -- no host round trip.  ``theta`` is updated in place.
     Returns energy[N] after the last sweep."""
-    shifts = ROTO6_SHIFTS if double else ROTO3_SHIFTS
-    P = theta.shape[1]
-    for _ in range(n_sweeps):
-        for i in range(P):
-            costs = energy_theta(program, theta, H, coord=i, shifts=shifts, dtype=dtype)
-            rotosolve_fit(costs.to(torch.float64), theta, i)
-    return energy_theta(program, theta, H, dtype=dtype)
+    if not (isinstance(theta, torch.Tensor) and theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
+        raise ValueError("theta must be a contiguous float64 CUDA tensor (updated in place)")
+    N, P = theta.shape
+    Hd = _hdev(H, dtype, theta.device)
+    e = torch.empty((N,), dtype=_RDT[dtype], device=theta.device)
+    ops = program.c_ops()
+    with torch.cuda.device(theta.device):
+        L.check(L.load().qmps_rotosolve_sweep(ops, len(program), program.nq, N, P, _p(theta), _p(Hd), int(n_sweeps),
+                                              int(bool(double)), _p(e), _CDT[dtype], _stream()), "rotosolve_sweep")
+    return e
 
 
 # ---- a11 pipeline ------------------------------------------------------------------------
-def loschmidt_costs(program, theta, A0, W, dtype=torch.complex128):
+def loschmidt_costs(program, theta, A0, W, dtype=torch.complex128, want_status=False):
     """cost[p, k] = -sqrt|eta_2|, echo[p, k] = -log|eta_2|^2 with eta_2 the leading eigenvalue
     of Map(W_k . merge(A0, A0), merge(B_p, B_p))  (qmps/loschmidts/time_evo.py:75-116).
 
     theta[NP, P] parameter sets, A0[2, D, D] the state being evolved, W[NT, 4, 4] two-site
-    gates (one per time).  Four launches: ansatz, merge, gate-merge, fixed points."""
-    B = ansatz_tensors(program, theta, dtype=dtype)
-    MB = merge(B, B)
-    A0 = _cdev(A0, dtype, B.device).reshape(1, *A0.shape[-3:])
-    W = _cdev(W, dtype, B.device)
+    gates (one per time).  One C-ABI call (``qmps_loschmidt_batched``: ansatz, merge, gate-merge,
+    fixed points on one stream); outputs are [NP, NT]."""
+    theta = _rdev(theta)
+    NP, P = theta.shape
+    A0 = _cdev(A0, dtype, theta.device).reshape(*A0.shape[-3:]).contiguous()
+    W = _cdev(W, dtype, theta.device)
     if W.dim() == 2:
         W = W[None]
-    WMA = merge(A0, A0, W)
-    fp = fixed_point(WMA, MB, pair="outer", want_vec=False)
-    # outputs are [NT, NP]; the reference indexes parameter sets first
-    return fp.cost.transpose(0, 1), fp.echo.transpose(0, 1), fp.eta.transpose(0, 1)
+    W = W.contiguous()
+    NT = W.shape[0]
+    rd = _RDT[dtype]
+    cost = torch.empty((NP, NT), dtype=rd, device=theta.device)
+    echo = torch.empty((NP, NT), dtype=rd, device=theta.device)
+    eta = torch.empty((NP, NT), dtype=dtype, device=theta.device)
+    st = torch.empty((NP, NT), dtype=torch.int32, device=theta.device) if want_status else None
+    ops = program.c_ops()
+    with torch.cuda.device(theta.device):
+        L.check(L.load().qmps_loschmidt_batched(ops, len(program), program.nq, NP, P, _p(theta), _p(A0), NT, _p(W),
+                                                _p(cost), _p(echo), _p(eta), _p(st), _CDT[dtype], _stream()),
+                "loschmidt_batched")
+    return (cost, echo, eta, st) if want_status else (cost, echo, eta)
+
+
+def loschmidt_costs_host(program, theta, A0, W, dtype=np.complex128, device=0, want_echo=True):
+    """``loschmidt_costs`` on HOST arrays through ``qmps_loschmidt_batched_host`` (numpy in, numpy out; the
+    copies are part of the call): theta[NP, P] float64, A0[2, D, D], W[NT, 4, 4] -> cost[NP, NT] (, echo)."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    A0 = np.ascontiguousarray(A0, dtype=dtype)
+    W = np.ascontiguousarray(W, dtype=dtype).reshape(-1, 4, 4)
+    NP, P = theta.shape
+    NT = W.shape[0]
+    rd = np.float64 if np.dtype(dtype) == np.complex128 else np.float32
+    cost = np.empty((NP, NT), dtype=rd)
+    echo = np.empty((NP, NT), dtype=rd) if want_echo else None
+    ops = program.c_ops()
+    L.check(L.require_device().qmps_loschmidt_batched_host(
+        ops, len(program), program.nq, NP, P, theta.ctypes.data, A0.ctypes.data, NT, W.ctypes.data, cost.ctypes.data,
+        echo.ctypes.data if want_echo else None, None, None, L.C128 if np.dtype(dtype) == np.complex128 else L.C64, int(device)),
+        "loschmidt_batched_host")
+    return (cost, echo) if want_echo else cost
+
+
+def energy_theta_host(program, theta, H, coord=None, shifts=None, dtype=np.complex128, device=0):
+    """``energy_theta`` on HOST arrays through ``qmps_energy_theta_host``: 8 P bytes in, 8 bytes per shift out."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    Hh = np.ascontiguousarray(H, dtype=dtype)
+    N, P = theta.shape
+    ns = 0 if shifts is None else len(shifts)
+    sh = np.ascontiguousarray(shifts, dtype=np.float64) if ns else None
+    rd = np.float64 if np.dtype(dtype) == np.complex128 else np.float32
+    e = np.empty((N, ns) if ns else (N,), dtype=rd)
+    ops = program.c_ops()
+    L.check(L.require_device().qmps_energy_theta_host(
+        ops, len(program), program.nq, N, P, theta.ctypes.data, Hh.ctypes.data, -1 if coord is None else int(coord),
+        sh.ctypes.data if ns else None, ns, e.ctypes.data, None, L.C128 if np.dtype(dtype) == np.complex128 else L.C64,
+        int(device)), "energy_theta_host")
+    return e
 
 
 def overlap_theta(program, theta1, theta2, dtype=torch.complex128):

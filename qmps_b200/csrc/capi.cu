@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 0 /* fp16_fast: measured slower than the generic kernel (profiles/README.md) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 7 /* fp16_fast: D = 4 eigenvalue-only kernel; 0 generic, 1/2 half-warp registers, 3-5 quarter-warp registers, 6 shared-resident, 7 shared-resident quarter-warp (measured best: profiles/exp_fp16_r02f.jsonl) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
@@ -216,7 +216,8 @@ int qmps_fixed_point_ex(int d, int D, int64_t NA, const void* A, int64_t NB, con
   FpParams p;
   memset(&p, 0, sizeof(p));
   p.d = d; p.D = D; p.NA = NA; p.NB = NB; p.A = A; p.B = B; p.pair_mode = pair_mode; p.left = left;
-  p.N = pair_mode == 1 ? NA * NB : (NA > NB ? NA : NB);
+  if (pair_mode < 0 || pair_mode > 2) return fail(QMPS_ERR_ARG, "fixed_point: pair_mode must be 0, 1 or 2");
+  p.N = pair_mode != 0 ? NA * NB : (NA > NB ? NA : NB);
   p.vec_gauge = vec_gauge;
   p.eta = eta; p.vec = vec; p.cost = cost; p.echo = echo; p.fid = fid; p.status = status;
   if (dtype == QMPS_C128) return fixed_point_f64(p, (cudaStream_t)stream);

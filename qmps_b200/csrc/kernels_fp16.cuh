@@ -151,6 +151,7 @@ fp16_kernel(FpParams p) {
     if (!live) pid = p.N - 1;
     int64_t ia, ib;
     if (p.pair_mode == 1) { ia = pid / p.NB; ib = pid - ia * p.NB; }
+    else if (p.pair_mode == 2) { ib = pid / p.NA; ia = pid - ib * p.NA; }
     else { ia = pid < p.NA ? pid : p.NA - 1; ib = pid < p.NB ? pid : p.NB - 1; }
     const cx<T>* Ag = reinterpret_cast<const cx<T>*>(p.A) + ia * tsz;
     const cx<T>* Bg = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;

@@ -224,6 +224,7 @@ fixed_point_kernel(FpParams p) {
   for (int64_t pid = (int64_t)blockIdx.x * gpc + gi; pid < p.N; pid += (int64_t)gridDim.x * gpc) {
     int64_t ia, ib;
     if (p.pair_mode == 1) { ia = pid / p.NB; ib = pid - ia * p.NB; }
+    else if (p.pair_mode == 2) { ib = pid / p.NA; ia = pid - ib * p.NA; }
     else { ia = pid < p.NA ? pid : p.NA - 1; ib = pid < p.NB ? pid : p.NB - 1; }
     const cx<T>* A = reinterpret_cast<const cx<T>*>(p.A) + ia * tsz;
     const cx<T>* B = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;

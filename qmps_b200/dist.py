@@ -6,7 +6,7 @@ for the host-logic tests).
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "global_argmin", "global_sum"]
+__all__ = ["shard_range", "global_argmin", "global_sum", "nccl_comm_ptr", "argmin_allreduce"]
 
 
 def shard_range(n_total, rank=None, world=None):
@@ -45,3 +45,40 @@ def global_sum(x):
         x = x.clone()
         dist.all_reduce(x, op=dist.ReduceOp.SUM)
     return x
+
+
+def nccl_comm_ptr(device=None, group=None):
+    """The raw ``ncclComm_t`` of torch's NCCL process group for ``device`` (as an int), or 0 when there is no
+    multi-rank NCCL group.  Passed to ``qmps_argmin_allreduce`` so that the C ABI issues the collective itself,
+    on the caller's stream, with the communicator torch already built."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return 0
+    pg = group if group is not None else dist.distributed_c10d._get_default_group()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    backend = pg._get_backend(device)
+    if not hasattr(backend, "_comm_ptr"):
+        raise RuntimeError("the process group's backend does not expose an NCCL communicator")
+    ptr = int(backend._comm_ptr())
+    if ptr == 0:                     # communicators are created lazily: one tiny collective builds it
+        dist.all_reduce(torch.zeros(1, device=device), group=group)
+        ptr = int(backend._comm_ptr())
+    return ptr
+
+
+def argmin_allreduce(cost, index_offset=0, comm=None):
+    """(min cost, global argmin) over the shards of all ranks in ONE C-ABI call (``qmps_argmin_allreduce``):
+    local reduction, a 16-byte-per-rank ncclAllGather and the final pass, stream-ordered on the current stream.
+    ``cost``: float64 CUDA vector (this rank's shard); returns two 1-element CUDA tensors."""
+    from . import _lib as L
+    cost = cost.reshape(-1)
+    if not (cost.is_cuda and cost.dtype == torch.float64 and cost.is_contiguous()):
+        raise ValueError("cost must be a contiguous float64 CUDA tensor")
+    bc = torch.empty((1,), dtype=torch.float64, device=cost.device)
+    bi = torch.empty((1,), dtype=torch.int64, device=cost.device)
+    if comm is None:
+        comm = nccl_comm_ptr(cost.device)
+    with torch.cuda.device(cost.device):
+        L.check(L.load().qmps_argmin_allreduce(comm or None, cost.numel(), cost.data_ptr() if cost.numel() else None,
+                                               int(index_offset), bc.data_ptr(), bi.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "argmin_allreduce")
+    return bc, bi

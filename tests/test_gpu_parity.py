@@ -194,24 +194,31 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
         Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt[::-1]).reshape(count, 4, 4, 4))
     Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
     lib = L.load()
-    slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)      # default: generic shared-memory kernel
-    lib.qmps_set_option(b"fp16_fast", 1)
+    default = B.fixed_point(Ad, Bd, left=left, want_vec=False)   # default: shared-resident quarter-warp kernel
+    lib.qmps_set_option(b"fp16_fast", 0)
     try:
-        fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
-        f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
-        t.cuda.synchronize()
+        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)  # generic shared-memory group kernel
     finally:
-        lib.qmps_set_option(b"fp16_fast", 0)
-    assert int(fast.status.abs().sum()) == 0
-    assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
-    for k in range(count):
-        x0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])[0]
-        assert abs(abs(fast.eta[k].item()) - abs(x0)) < TOL
-        assert abs(fast.cost[k].item() + np.sqrt(abs(x0))) < TOL
-        w = np.linalg.eigvals(O.transfer_matrix(A[k], Bt[k]))
-        lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
-        assert np.abs(w - lam).min() < 1e-11               # it IS an eigenvalue of E, not just the right modulus
-    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5      # complex64 mode
+        lib.qmps_set_option(b"fp16_fast", 7)
+    assert (default.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
+    for variant in (1, 3, 6, 7):       # half-warp / quarter-warp register forms, shared-resident half / quarter warp
+        lib.qmps_set_option(b"fp16_fast", variant)
+        try:
+            fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+            f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
+            t.cuda.synchronize()
+        finally:
+            lib.qmps_set_option(b"fp16_fast", 7)
+        assert int(fast.status.abs().sum()) == 0
+        assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
+        for k in range(count):
+            x0 = (O.left_fixed_point if left else O.right_fixed_point)(A[k], Bt[k])[0]
+            assert abs(abs(fast.eta[k].item()) - abs(x0)) < TOL
+            assert abs(fast.cost[k].item() + np.sqrt(abs(x0))) < TOL
+            w = np.linalg.eigvals(O.transfer_matrix(A[k], Bt[k]))
+            lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
+            assert np.abs(w - lam).min() < 1e-11               # it IS an eigenvalue of E, not just the right modulus
+        assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5      # complex64 mode
 
 
 @pytest.mark.parametrize("left", [False, True])
@@ -267,13 +274,13 @@ def test_fixed_point_d4_degenerate_inputs(env):
     zero = np.zeros((1, 2, 4, 4), complex)
     X = t.from_numpy(np.concatenate([A, prod, zero])).cuda()
     lib = env["L"].load()
-    for fast in (0, 1):
+    for fast in (0, 1, 3, 6, 7):
         lib.qmps_set_option(b"fp16_fast", fast)
         try:
             fp = B.fixed_point(X, X, want_vec=False)
             eta = fp.eta.cpu().numpy()
         finally:
-            lib.qmps_set_option(b"fp16_fast", 0)
+            lib.qmps_set_option(b"fp16_fast", 7)
         assert np.abs(np.abs(eta[:4]) - 1).max() < 1e-12
         assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
 
