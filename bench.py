@@ -10,6 +10,11 @@ Workload (BASELINE.json configs[1]): batched exact environment solve, D = 2, d =
 own 2^20-problem shard (weak scaling, no data-path collective); the time is the max over
 ranks of a CUDA-event measurement bracketed by barrier + synchronize.
 
+The other cells of BASELINE.json's metric (Loschmidt-echo steps/s at D = 2 and 4, D = 8 energy evaluations, D = 64 / 256
+transfer-matrix applications, both precisions, and a 2^24 steady-state batch) are `sub_results` of the same line, each with
+its own roofline, e2e and cpu_baseline (tools/bench_legs.py).  Config 4 runs at every N as STRONG scaling with the
+NCCL argmin inside its timed region.
+
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -26,10 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_PER_GPU = 1 << 20
-ALGO_BYTES_PER_SOLVE = 128 + 16 + 64            # A in, eta + r out
+# A in (128) + eta (16) + r (64) + C (64) + status (4): everything get_env_exact's chain produces that is unique
+ALGO_BYTES_PER_SOLVE = 128 + 16 + 64 + 64 + 4            # SURVEY 8(d) + the Cholesky factor and the failure flag
 METRIC = "environment_solves_per_sec"
 UNIT = "solves/s"
 WORKLOAD = "exact_env_D2_d2_c128_2^20_per_gpu"
+OUTPUTS = "eta[N], r[N,2,2] (Hermitian, trace 1), C[N,2,2] (lower Cholesky factor, r = C C^dagger, i.e. V[:,0] up to its norm), status[N]"
 
 
 _JSON_OUT = None
@@ -115,7 +122,9 @@ def _cpu_worker(args):
     Us = [unitary_group.rvs(4, random_state=seed * 100003 + k) for k in range(64)]
     t0 = time.perf_counter()
     for k in range(count):
-        O.get_env_exact(Us[k & 63])        # unitary_to_tensor -> eigs -> cholesky -> environment_to_unitary
+        # the same unit of work as the GPU arm: U -> A -> (eta, r) by dense eig -> C by cholesky -> V[:,0]
+        # (qmps/tools.py:176-182 without the null_space completion of V, whose columns are not unique)
+        O.env_exact_parts(O.unitary_to_tensor(Us[k & 63]))
     return time.perf_counter() - t0
 
 
@@ -154,12 +163,13 @@ def run_reference(args):
     # stays near two minutes whatever K is: a calibration on the warmed-up pool gives the per-core rate
     warm = min(args.warmup, 2)
     rate, cores, sec, per_core = cpu_reference_rate(None, steps=args.steps, warmup=warm, budget_s=120.0)
-    sample = f"{per_core} per-call get_env_exact solves per core per step on {cores} cores (oracle port of qmps/tools.py:176-182; numpy eig + scipy cholesky + null_space)"
+    sample = (f"{per_core} per-call solves per core per step on {cores} cores: unitary_to_tensor -> dense eig -> Hermitian trace-1 r "
+              f"-> cholesky -> V[:,0] (oracle port of qmps/tools.py:176-182; same outputs as the GPU arm: {OUTPUTS})")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample, "outputs": OUTPUTS},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -195,15 +205,21 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = L.require_device()
     N = N_PER_GPU
-    NBUF = 4          # rotate inputs: 4 x 128 MiB, far larger than the 126 MB L2
+    NBUF = 4          # rotate inputs AND outputs: 4 x 128 MiB in, 4 x 148 MiB out, each far larger than the 126 MB L2
     A = [make_tensors(torch, N, 1 + 17 * rank + b, dev) for b in range(NBUF)]
-    eta = torch.empty((N,), dtype=torch.complex128, device=dev)
-    r = torch.empty((N, 2, 2), dtype=torch.complex128, device=dev)
+    eta = [torch.empty((N,), dtype=torch.complex128, device=dev) for _ in range(NBUF)]
+    r = [torch.empty((N, 2, 2), dtype=torch.complex128, device=dev) for _ in range(NBUF)]
+    C = [torch.empty((N, 2, 2), dtype=torch.complex128, device=dev) for _ in range(NBUF)]
+    status = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     stream = torch.cuda.current_stream().cuda_stream
 
+    def launch(i, st):
+        b = i % NBUF
+        L.check(lib.qmps_env_exact(2, 2, N, A[b].data_ptr(), 0, 1, eta[b].data_ptr(), r[b].data_ptr(), C[b].data_ptr(),
+                                   status[b].data_ptr(), L.C128, st), "env_exact")
+
     def step(i):
-        L.check(lib.qmps_env_exact(2, 2, N, A[i % NBUF].data_ptr(), 0, 1, eta.data_ptr(), r.data_ptr(), None, None,
-                                   L.C128, stream), "env_exact")
+        launch(i, stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -211,7 +227,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # clock ramp: ~0.3 s of untimed launches so that the timed region (K x ~35 us) does not start on idle clocks
+    # clock ramp: ~0.3 s of untimed launches so that the timed region (K x ~45 us) does not start on idle clocks
     t_end = time.time() + 0.3
     i = 0
     while time.time() < t_end:
@@ -219,30 +235,10 @@ def run_ours(args):
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
-    # The K steps are K kernel launches of ~35 us each: the host (ctypes call + driver) can pace them.
-    # Capture the K launches (input rotation included) once into a CUDA graph and time its replay;
-    # the direct-launch timing is kept beside it.  Falls back to direct launches if capture is refused.
-    graph, launch_mode = None, "direct"
-    if not args.no_graph:
-        try:
-            cap_stream = torch.cuda.Stream()
-            cap_stream.wait_stream(torch.cuda.current_stream())
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cap_stream):
-                cs = torch.cuda.current_stream().cuda_stream
-                for i in range(args.steps):
-                    L.check(lib.qmps_env_exact(2, 2, N, A[i % NBUF].data_ptr(), 0, 1, eta.data_ptr(), r.data_ptr(),
-                                               None, None, L.C128, cs), "env_exact (capture)")
-            g.replay(); g.replay()
-            torch.cuda.synchronize()
-            graph, launch_mode = g, "cuda_graph"
-        except Exception as e:  # noqa: BLE001 - any capture failure -> direct launches, reported in config
-            launch_mode = f"direct (graph capture refused: {type(e).__name__})"
-            torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # two events around the K back-to-back launches (an event between launches would serialise them)
+    # `value`: K direct launches through the C ABI (the public call), two events around them
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -251,20 +247,27 @@ def run_ours(args):
     ev1.record()
     barrier()
     direct_ms = ev0.elapsed_time(ev1)
-    total_ms = direct_ms
-    if graph is not None:
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev2.record()
-        graph.replay()
-        ev3.record()
-        barrier()
-        graph_ms = ev2.elapsed_time(ev3)
-        if graph_ms <= direct_ms:
-            total_ms = graph_ms
-        else:
-            launch_mode = "direct (graph replay was slower: %.4f ms/step)" % (graph_ms / args.steps)
-    per_launch_ms = [total_ms / args.steps]
+    # reported beside it, never substituted: the same K launches captured once into a CUDA graph
+    graph_ms = None
+    if not args.no_graph:
+        try:
+            cap_stream = torch.cuda.Stream()
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_stream):
+                cs = torch.cuda.current_stream().cuda_stream
+                for i in range(args.steps):
+                    launch(i, cs)
+            g.replay()
+            torch.cuda.synchronize()
+            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev2.record(); g.replay(); ev3.record()
+            barrier()
+            graph_ms = ev2.elapsed_time(ev3)
+        except Exception as e:  # noqa: BLE001 - capture refused: reported, the direct timing stands
+            graph_ms = f"capture refused: {type(e).__name__}"
+            torch.cuda.synchronize()
     # keep the GPU busy a little longer so that the clock sampler has samples under load
     if rank == 0:
         t_end = time.time() + 0.6
@@ -272,22 +275,25 @@ def run_ours(args):
             step(0)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([direct_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
     value = world * N * args.steps / (total_ms_max * 1e-3)
+    n_bad = int((status[0] != 0).sum().item())
 
     # ---- e2e: the host-buffer C ABI call, pinned host memory, copies inside the timed region
     hin = torch.empty((N, 2, 2, 2), dtype=torch.complex128).pin_memory()
     hin.copy_(A[0])
     heta = torch.empty((N,), dtype=torch.complex128).pin_memory()
     hr = torch.empty((N, 2, 2), dtype=torch.complex128).pin_memory()
+    hC = torch.empty((N, 2, 2), dtype=torch.complex128).pin_memory()
+    hst = torch.empty((N,), dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
-        L.check(lib.qmps_env_exact_host(2, 2, N, hin.data_ptr(), 0, 1, heta.data_ptr(), hr.data_ptr(), None, None,
-                                        L.C128, local_rank), "env_exact_host")
+        L.check(lib.qmps_env_exact_host(2, 2, N, hin.data_ptr(), 0, 1, heta.data_ptr(), hr.data_ptr(), hC.data_ptr(),
+                                        hst.data_ptr(), L.C128, local_rank), "env_exact_host")
 
     e2e_step(); e2e_step()
     barrier()
@@ -302,9 +308,9 @@ def run_ours(args):
     e2e_value = world * N * e2e_steps / float(te.item())
     step(0)                                   # same input through the device-pointer entry: identical bits
     torch.cuda.synchronize()
-    assert torch.equal(hr.to(dev), r) and torch.equal(heta.to(dev), eta), "host-buffer path disagrees with device path"
-    # what the link alone allows: the same bytes (128 B in, 80 B out per solve) as plain pinned copies, both
-    # directions at once on two streams, no kernel
+    assert torch.equal(hr.to(dev), r[0]) and torch.equal(heta.to(dev), eta[0]) and torch.equal(hC.to(dev), C[0]), \
+        "host-buffer path disagrees with device path"
+    # what the link alone allows: the same bytes as plain pinned copies, both directions at once, no kernel
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     din = torch.empty_like(A[0])
 
@@ -312,8 +318,10 @@ def run_ours(args):
         with torch.cuda.stream(s_in):
             din.copy_(hin, non_blocking=True)
         with torch.cuda.stream(s_out):
-            heta.copy_(eta, non_blocking=True)
-            hr.copy_(r, non_blocking=True)
+            heta.copy_(eta[0], non_blocking=True)
+            hr.copy_(r[0], non_blocking=True)
+            hC.copy_(C[0], non_blocking=True)
+            hst.copy_(status[0], non_blocking=True)
 
     link_step()
     torch.cuda.synchronize()
@@ -322,41 +330,121 @@ def run_ours(args):
         link_step()
     torch.cuda.synchronize()
     link_value = N * 5 / (time.perf_counter() - t0)
-    del din
+    del din, hin, heta, hr, hC, hst
+
+    # ---- the other cells of the metric
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_legs as BL
+    from qmps_b200 import batched as B, represent as R, dist as QD
+    peaks = BL.load_peaks()
+    subs, sub_errors = [], []
+
+    def leg(name, fn):
+        try:
+            out = fn()
+            if out is not None:
+                subs.append(out)
+        except Exception as e:  # noqa: BLE001 - a failing leg must not take the headline line with it
+            sub_errors.append(f"{name}: {type(e).__name__}: {e}"[:300])
+            torch.cuda.synchronize()
+
+    if not args.no_sub:
+        del A[1:], eta[1:], r[1:], C[1:], status[1:]
+        torch.cuda.empty_cache()
+        # config 4, strong scaling with the collective inside the timed region: runs at every N
+        raw = {}
+
+        def cfg4():
+            raw.update(BL.leg_energy_d8(torch, B, R, QD, dev, peaks, rank, world, scale=args.sub_scale))
+            t4 = torch.tensor([raw["ms"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            res = BL.finish_energy_d8(torch, B, raw, float(t4.item()), world, peaks)
+            if rank == 0:
+                th = raw["theta_h"]
+                ms_e = BL.wall_ms(lambda: B.energy_theta_host(raw["prog"], th, raw["H"], coord=5, shifts=B.ROTO3_SHIFTS, device=local_rank), reps=2, warm=1)
+                res["e2e"] = {"value": 3 * len(th) / ms_e * 1e3, "unit": "evals/s", "h2d_bytes_per_step": th.nbytes, "d2h_bytes_per_step": 3 * 8 * len(th),
+                              "api": "qmps_energy_theta_host (rank 0's shard, pageable numpy buffers)", "n_gpus": 1}
+            return res
+        leg("cfg4", cfg4)
+        if world == 1:
+            def steady():
+                n24 = 1 << 24
+                Abig = make_tensors(torch, n24, 99, dev)
+                o_eta = torch.empty((n24,), dtype=torch.complex128, device=dev); o_r = torch.empty((n24, 2, 2), dtype=torch.complex128, device=dev)
+                o_C = torch.empty((n24, 2, 2), dtype=torch.complex128, device=dev); o_st = torch.empty((n24,), dtype=torch.int32, device=dev)
+                fn = lambda: L.check(lib.qmps_env_exact(2, 2, n24, Abig.data_ptr(), 0, 1, o_eta.data_ptr(), o_r.data_ptr(), o_C.data_ptr(),
+                                                        o_st.data_ptr(), L.C128, stream), "env_exact")
+                ms = BL.timed_ms(torch, fn, reps=5, warm=2)
+                ach = ALGO_BYTES_PER_SOLVE * n24 / (ms * 1e-3) / 1e9
+                return {"cfg": 2, "workload": "exact_env_D2_c128_2^24_one_launch (steady state)", "metric": METRIC, "unit": UNIT, "dtype": "c128",
+                        "value": n24 / ms * 1e3, "ms_per_step": ms, "units_per_step": n24,
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                                     "kernel": "env_d2_stream_kernel<false,true>", "algorithmic_per_unit": f"{ALGO_BYTES_PER_SOLVE} B", "traffic": None}}
+            leg("cfg2_steady", steady)
+            torch.cuda.empty_cache()
+            leg("cfg7", lambda: BL.leg_loschmidt(torch, B, R, dev, 2, peaks, scale=args.sub_scale))
+            leg("cfg3", lambda: BL.leg_loschmidt(torch, B, R, dev, 4, peaks, scale=args.sub_scale))
+            for D in (64, 256):
+                for tag in ("c128", "c64"):
+                    leg(f"cfg5_D{D}_{tag}", lambda D=D, tag=tag: BL.leg_power(torch, B, dev, D, peaks, tag, scale=args.sub_scale))
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        k_ms = float(np.mean(per_launch_ms))
+        k_ms = direct_ms / args.steps
         achieved = ALGO_BYTES_PER_SOLVE * N / (k_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": WORKLOAD, "D": 2, "d": 2, "solves_per_gpu_per_step": N,
-                       "input": "A[N,2,2,2] complex128 resident in HBM (128 B/solve), outputs eta[N], r[N,2,2]",
-                       "l2_policy": f"inputs rotate over {NBUF} distinct 128 MiB buffers (>126 MB L2), outputs 80 MiB",
+                       "input": "A[N,2,2,2] complex128 resident in HBM (128 B/solve)", "outputs": OUTPUTS,
+                       "l2_policy": f"inputs AND outputs rotate over {NBUF} distinct buffer sets (128 MiB in, 148 MiB out each; L2 is 126 MB)",
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "launch": launch_mode, "direct_launch_ms_per_step": direct_ms / args.steps,
+                       "launch": "direct C-ABI launches (value); the same K launches as one CUDA-graph replay are reported in graph_ms_per_step",
+                       "graph_ms_per_step": (graph_ms / args.steps) if isinstance(graph_ms, float) else graph_ms,
+                       "failed_problems_in_batch": n_bad,
                        "prewarm": "0.3 s of untimed launches before the W warm-up steps (clock ramp)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                         "kernel": "env_d2_stream_kernel<false,false>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SOLVE * N,
+                         "kernel": "env_d2_stream_kernel<false,true>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SOLVE * N,
+                         "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE,
                          "kernel_ms": k_ms, "traffic": dram_traffic_from_profile(),
-                         "traffic_note": "ncu --set full, one launch: DRAM reads 134.2 MB = the algorithmic 128 B/solve; "
-                                         "DRAM writes 38.5 MB < 83.9 MB algorithmic because part of the output is still "
-                                         "dirty in the 126 MB L2 when the launch ends (profiles/roofline_traffic.json)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * N, "d2h_bytes_per_step": 80 * N,
-                    "steps": e2e_steps, "api": "qmps_env_exact_host (C ABI, pinned host buffers, chunked 3-stream pipeline)",
+                         "traffic_note": "ncu --set full, one launch of this kernel with rotated outputs: dram__bytes_read.sum + dram__bytes_write.sum (profiles/roofline_traffic.json)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * N, "d2h_bytes_per_step": 148 * N,
+                    "steps": e2e_steps, "api": "qmps_env_exact_host (C ABI, pinned host buffers, chunked 3-stream pipeline), all four outputs",
                     "link_bound_per_gpu": link_value,
                     "link_bound_note": "same H2D+D2H bytes as plain concurrent pinned copies, no kernel (solves/s, rank 0)"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
+            "sub_results": subs,
         }
+        if sub_errors:
+            line["sub_errors"] = sub_errors
         if world == 1 and not args.no_cpu:
-            # a bounded sample: one untimed warm-up map (imports, page-in), then ~15 s of per-call solves
-            rate, cores, _, pc = cpu_reference_rate(per_core=None, steps=4, warmup=1, budget_s=15.0, max_per_core=16384)
+            # bounded samples: one untimed warm-up map (imports, page-in), then ~12 s of per-call solves
+            rate, cores, _, pc = cpu_reference_rate(per_core=None, steps=4, warmup=1, budget_s=12.0, max_per_core=16384)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"4 x {pc} per-call get_env_exact solves per core on {cores} cores (oracle port of qmps/tools.py:176-182)"}
+                                    "sample": f"4 x {pc} per-call solves per core on {cores} cores (oracle port of qmps/tools.py:176-182: "
+                                              f"unitary_to_tensor, dense eig, cholesky, V[:,0] -- the outputs the GPU arm writes)"}
+            kinds = ["env_d2", "loschmidt_d2", "loschmidt_d4", "energy_d8", "power_d64", "power_d256"]
+            try:
+                cb, cores2 = BL.cpu_baselines(kinds, seconds=args.cpu_seconds)
+                line["cpu_baseline"]["vectorised_value"] = cb["env_d2"]["vectorised"]
+                line["cpu_baseline"]["vectorised_note"] = "BASELINE.md B2: the same algorithm as stacked numpy.linalg calls (oracle/stacked.py), one process per core"
+                key = {7: "loschmidt_d2", 3: "loschmidt_d4", 4: "energy_d8"}
+                for sres in subs:
+                    k = key.get(sres["cfg"])
+                    if sres["cfg"] == 5:
+                        k = "power_d64" if "_D64_" in sres["workload"] else "power_d256"
+                    if sres["cfg"] == 2:
+                        k = "env_d2"
+                    if k:
+                        sres["cpu_baseline"] = {"value": cb[k]["port"], "vectorised_value": cb[k]["vectorised"], "unit": sres["unit"], "cores": cores2,
+                                                "kind": "port", "sample": f"{args.cpu_seconds:.0f} s of per-call oracle evaluations per core (port); "
+                                                                          f"{args.cpu_seconds:.0f} s of stacked / threaded numpy (vectorised)"}
+            except Exception as e:  # noqa: BLE001
+                line["sub_errors"] = line.get("sub_errors", []) + [f"cpu_baselines: {type(e).__name__}: {e}"[:300]]
         emit(line)
     if world > 1:
         dist.barrier()
@@ -371,6 +459,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time direct launches only (no CUDA-graph replay)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub_results legs (Loschmidt D=2/4, D=8 energy, D=64/256 power method)")
+    ap.add_argument("--sub-scale", type=float, default=1.0, help="shrink the sub_results workloads (smoke runs)")
+    ap.add_argument("--cpu-seconds", type=float, default=2.0, help="length of each CPU baseline sample of the sub_results")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." at
     # communicator creation, torchrun children inherit the descriptor): keep the real stdout aside for the JSON
