@@ -325,6 +325,25 @@ int qmps_nccl_unique_id(void* id128);                                        /* 
 int qmps_nccl_comm_create(const void* id128, int world, int rank, void** comm);   /* ncclCommInitRank on the current device */
 int qmps_nccl_comm_destroy(void* comm);
 
+
+/* (f)-3 classical iTDVP of single-site uniform MPS, batched over N independent states (xmps iMPS.dA_dt /
+ *     iTDVP.Trajectory; call sites scripts/classical_time_evolution.py:16-27, qmps/loschmidts/mps_loschmidts.py:20-22,
+ *     scripts/mixed_environment.py:41).  h [d*d][d*d] is the two-site Hamiltonian (DEVICE), D <= 16 (any), d <= 4.
+ *     imaginary = 1 replaces -i by -1 (imaginary-time flow towards the ground state).
+ *     tangent: AL [N][d][D][D] LEFT-CANONICAL -> dA [N][d][D][D], energy [N] (real, <h> per bond), status [N].
+ *     dadt:    A in ANY gauge (canonicalise, tangent, transform back: the left gauge condition is covariant). */
+int qmps_tdvp_tangent(int d, int D, int64_t N, const void* AL, const void* h, int imaginary, void* dA, void* energy,
+                      int32_t* status, int dtype, void* stream);
+int qmps_tdvp_dadt(int d, int D, int64_t N, const void* A, const void* h, int imaginary, void* dA, void* energy,
+                   int32_t* status, int dtype, void* stream);
+/* n_steps steps of size dt from A_io (replaced by its canonical form, then by the final state), no host round trip:
+ *     method 1 = the reference's RK4 loop (classical_time_evolution.py:22-26, left_canonicalise after each step),
+ *     method 0 = explicit Euler (Trajectory.eulerint).  Optional outputs: traj [n_steps+1][N][d][D][D],
+ *     rates [n_steps+1][N] = -log|eta(E_{A_t A_0})|^2 (Trajectory.loschmidts()), energy [n_steps][N] (at the start
+ *     of each step). */
+int qmps_tdvp_evolve(int d, int D, int64_t N, void* A_io, const void* h, double dt, int n_steps, int method, int imaginary,
+                     void* traj, void* rates, void* energy, int32_t* status, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

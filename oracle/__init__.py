@@ -56,3 +56,4 @@ from .costs import *        # noqa: F401,F403
 from .canonical import *    # noqa: F401,F403
 from .brickwall import *    # noqa: F401,F403
 from .stacked import *      # noqa: F401,F403
+from .tdvp import *         # noqa: F401,F403

@@ -52,6 +52,9 @@ SIGNATURES = {
     "qmps_nccl_unique_id": ([_vp], _i),
     "qmps_nccl_comm_create": ([_vp, _i, _i, _vp], _i),
     "qmps_nccl_comm_destroy": ([_vp], _i),
+    "qmps_tdvp_tangent": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_tdvp_dadt": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_tdvp_evolve": ([_i, _i, _i64, _vp, _vp, ctypes.c_double, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_merge": ([_i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_ansatz": ([_gp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp], _i),
     "qmps_energy_theta": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp], _i),

@@ -20,6 +20,7 @@ FixedPoint = namedtuple("FixedPoint", "eta vec cost echo fid status")
 RotoFit = namedtuple("RotoFit", "theta_star fit")
 Canonical = namedtuple("Canonical", "AL eta L status")
 Mixed = namedtuple("Mixed", "AL AR C eta status")
+TdvpRun = namedtuple("TdvpRun", "A traj rates energy status")
 
 _CDT = {torch.complex128: L.C128, torch.complex64: L.C64}
 _RDT = {torch.complex128: torch.float64, torch.complex64: torch.float32}
@@ -465,6 +466,43 @@ def tm_power(A, B, K, r0=None):
     with torch.cuda.device(A.device):
         L.check(L.load().qmps_tm_power(d, D, N, _p(A), _p(B), _p(r), int(K), _p(ray), _dt(A), _stream()), "tm_power")
     return r, ray
+
+
+# ---- classical iTDVP ------------------------------------------------------------
+def tdvp_dadt(A, h, imaginary=False, assume_left_canonical=False, want_status=False):
+    """``iMPS([A]).dA_dt([h])`` for a batch A[N, d, D, D] (xmps; call sites scripts/classical_time_evolution.py:22-26,
+    scripts/mixed_environment.py:41): the gauge-fixed TDVP tangent vector for the two-site Hamiltonian h[d*d, d*d].
+    Returns (dA[N, d, D, D], energy[N]) (+ status)."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    N, d, D, _ = A.shape
+    hd = _cdev(h, A.dtype, A.device).reshape(d * d, d * d).contiguous()
+    dA = torch.empty_like(A)
+    e = torch.empty((N,), dtype=_RDT[A.dtype], device=A.device)
+    st = torch.empty((N,), dtype=torch.int32, device=A.device) if want_status else None
+    fn = L.load().qmps_tdvp_tangent if assume_left_canonical else L.load().qmps_tdvp_dadt
+    with torch.cuda.device(A.device):
+        L.check(fn(d, D, N, _p(A), _p(hd), int(bool(imaginary)), _p(dA), _p(e), _p(st), _dt(A), _stream()), "tdvp_dadt")
+    return (dA, e, st) if want_status else (dA, e)
+
+
+def tdvp_evolve(A, h, dt, n_steps, method="rk4", imaginary=False, want_traj=False, want_rates=True, want_energy=True):
+    """``n_steps`` TDVP steps of size ``dt`` for a batch of states, one C-ABI call, no host round trip:
+    ``method='rk4'`` is the reference's loop (scripts/classical_time_evolution.py:21-27), ``'euler'`` is
+    ``Trajectory.eulerint`` (qmps/loschmidts/mps_loschmidts.py:22).  Returns ``TdvpRun(A_final, traj, rates, energy)``:
+    rates[t, n] = -log|eta(E_{A_t A_0})|^2 (``Trajectory.loschmidts()``), energy[t, n] at the start of step t."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128).clone()
+    N, d, D, _ = A.shape
+    hd = _cdev(h, A.dtype, A.device).reshape(d * d, d * d).contiguous()
+    rd = _RDT[A.dtype]
+    traj = torch.empty((n_steps + 1, N, d, D, D), dtype=A.dtype, device=A.device) if want_traj else None
+    rates = torch.empty((n_steps + 1, N), dtype=rd, device=A.device) if want_rates else None
+    en = torch.empty((n_steps, N), dtype=rd, device=A.device) if want_energy else None
+    st = torch.zeros((N,), dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_tdvp_evolve(d, D, N, _p(A), _p(hd), float(dt), int(n_steps), 1 if method == "rk4" else 0,
+                                          int(bool(imaginary)), _p(traj), _p(rates), _p(en), _p(st), _dt(A), _stream()),
+                "tdvp_evolve")
+    return TdvpRun(A, traj, rates, en, st)
 
 
 # ---- (e) -----------------------------------------------------------------------------

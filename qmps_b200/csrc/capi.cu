@@ -209,7 +209,7 @@ int qmps_fixed_point_ex(int d, int D, int64_t NA, const void* A, int64_t NB, con
                         int dtype, void* stream) {
   if (vec_gauge != QMPS_GAUGE_TRACE && vec_gauge != QMPS_GAUGE_ZGEEV) return fail(QMPS_ERR_ARG, "fixed_point: bad vec_gauge");
   if (NA < 0 || NB < 0 || (!A && NA) || (!B && NB)) return fail(QMPS_ERR_ARG, "fixed_point: bad arguments");
-  if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: D must be 1, 2, 4, 8 or 16");
+  if (D < 1 || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: D must be 1..16");
   if (d < 1 || d > 16) return fail(QMPS_ERR_UNSUPPORTED, "fixed_point: d must be 1..16");
   if (pair_mode == 0 && !(NA == NB || NA == 1 || NB == 1)) return fail(QMPS_ERR_ARG, "fixed_point: batch sizes do not broadcast");
   if (NA == 0 || NB == 0) return 0;

@@ -38,7 +38,7 @@ template <typename T> int launch_expect(const ExpectParams& p, cudaStream_t st) 
 
 int check_shape(const char* who, int d, int D, int64_t N, int dtype) {
   if (N < 0) return fail(QMPS_ERR_ARG, std::string(who) + ": negative batch");
-  if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, std::string(who) + ": D must be 1, 2, 4, 8 or 16");
+  if (D < 1 || D > 16) return fail(QMPS_ERR_UNSUPPORTED, std::string(who) + ": D must be 1..16");
   if (d < 1 || d > 4) return fail(QMPS_ERR_UNSUPPORTED, std::string(who) + ": d must be 1..4");
   if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, std::string(who) + ": bad dtype");
   return 0;

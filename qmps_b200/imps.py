@@ -90,6 +90,65 @@ class iMPS:
         o = other.data[0] if isinstance(other, iMPS) else np.asarray(other)
         return float(_np(batched.overlap(self.data[0][None], np.ascontiguousarray(o, dtype=np.complex128)[None]))[0])
 
+    # ---- TDVP (scripts/classical_time_evolution.py:22-26, scripts/mixed_environment.py:41) ----
+    def __sub__(self, other):
+        o = other.data[0] if isinstance(other, iMPS) else np.asarray(other)
+        return iMPS([self.data[0] - o])
+
+    def __mul__(self, c):
+        return iMPS([c * self.data[0]])
+
+    def __truediv__(self, c):
+        return iMPS([self.data[0] / c])
+
+    def dA_dt(self, H, imaginary=False):
+        """``mps.dA_dt([H])``: the TDVP tangent vector as an ``iMPS`` (so that ``mps + k1/2`` works as in the
+        reference's RK4 loop).  ``H`` is a list with one two-site Hamiltonian matrix."""
+        h = H[0] if isinstance(H, (list, tuple)) else H
+        dA, _, st = batched.tdvp_dadt(self.data[0][None], np.asarray(h, dtype=np.complex128), imaginary=imaginary,
+                                      want_status=True)
+        _raise_for(st, "dA_dt")
+        return iMPS([_np(dA)[0]])
+
+    def energy(self, H):
+        h = H[0] if isinstance(H, (list, tuple)) else H
+        return float(_np(batched.tdvp_dadt(self.data[0][None], np.asarray(h, dtype=np.complex128))[1])[0])
+
+
+class Trajectory:
+    """``xmps.iTDVP.Trajectory(mps_0=A, H=[h])`` as qmps/loschmidts/mps_loschmidts.py:20-22 uses it:
+    ``eulerint(T)`` / ``rk4int(T)`` integrate over the time grid ``T`` on the device in one call, ``loschmidts()``
+    returns -log|overlap with the initial state|^2 per site, ``mps_list()`` the stored states."""
+
+    def __init__(self, mps_0, H):
+        self.mps_0 = mps_0 if isinstance(mps_0, iMPS) else iMPS([mps_0])
+        self.H = H if isinstance(H, (list, tuple)) else [H]
+        self.run = None
+
+    def _integrate(self, T, method):
+        T = np.asarray(T, dtype=np.float64)
+        if len(T) < 2:
+            raise ValueError("need at least two time points")
+        dt = float(T[1] - T[0])
+        if not np.allclose(np.diff(T), dt):
+            raise ValueError("uniform time grids only")
+        self.run = batched.tdvp_evolve(self.mps_0.data[0][None], np.asarray(self.H[0], dtype=np.complex128), dt, len(T) - 1,
+                                       method=method, want_traj=True)
+        _raise_for(self.run.status, "Trajectory")
+        return self
+
+    def eulerint(self, T):
+        return self._integrate(T, "euler")
+
+    def rk4int(self, T):
+        return self._integrate(T, "rk4")
+
+    def loschmidts(self):
+        return _np(self.run.rates)[:, 0]
+
+    def mps_list(self):
+        return [iMPS([a]) for a in _np(self.run.traj)[:, 0]]
+
 
 class TransferMatrix:
     """``TransferMatrix(A).eigs() -> (eta, l, r)`` (qmps/tools.py:181): r Hermitian trace 1,

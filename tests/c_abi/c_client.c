@@ -19,7 +19,7 @@ int main(int argc, char** argv) {
   if (!version || !last_error || !fixed_point) return 4;
   if (!strstr(version(), "sm_100a")) return 5;
   /* bad bond dimension: rejected before any CUDA call, message available */
-  int rc = fixed_point(2, 3, 1, (const void*)1, 1, (const void*)1, 0, 0, 0, 0, 0, 0, 0, 0, QMPS_C128, 0);
+  int rc = fixed_point(2, 17, 1, (const void*)1, 1, (const void*)1, 0, 0, 0, 0, 0, 0, 0, 0, QMPS_C128, 0);
   if (rc != QMPS_ERR_UNSUPPORTED || !strstr(last_error(), "D must be")) return 6;
   /* empty batch: success */
   if (fixed_point(2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, QMPS_C128, 0) != 0) return 7;

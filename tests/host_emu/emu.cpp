@@ -14,6 +14,7 @@
 #include "../../qmps_b200/csrc/canon.cuh"
 #include "../../qmps_b200/csrc/brickwall.cuh"
 #include "../../qmps_b200/csrc/fp_d2.cuh"
+#include "../../qmps_b200/csrc/tdvp.cuh"
 
 using namespace qmps;
 typedef cx<double> zc;
@@ -302,6 +303,35 @@ int emu_bw_env_thread(int side, int bra_undaggered, int64_t N, const double* U1,
     status[p] = bw_env_thread<double>((const zc*)U1 + p * 16, (const zc*)U2 + p * 16, (const zc*)B1 + p * 16,
                                       (const zc*)B2 + p * 16, bra_undaggered, side, (zc*)mat + p * 16, (zc*)eta + p,
                                       (zc*)vec + p * 4);
+  return 0;
+}
+
+// TDVP tangent vector of left-canonical tensors (tdvp.cuh) and the gauge-back transform
+int emu_tdvp_tangent(int d, int D, int64_t N, const double* a, const double* h, int imaginary, double* out, double* energy,
+                     int32_t* status) {
+  const Grp g = solo();
+  const int n = D * D;
+  std::vector<zc> E((size_t)n * (n + 1)), x(n), r(n), K(n), rinv(n), Cc(n), Ci(n), Hl(n), AA((size_t)d * d * n), C((size_t)d * d * n),
+      G((size_t)d * n);
+  std::vector<int> step(n), done(n);
+  std::vector<double> red(4);
+  for (int64_t k = 0; k < N; ++k) {
+    double en = 0;
+    status[k] = tdvp_tangent_problem<double>(g, (const zc*)a + k * (size_t)(d * n), (const zc*)h, imaginary, d, D, E.data(), x.data(),
+                                             r.data(), K.data(), rinv.data(), Cc.data(), Ci.data(), Hl.data(), AA.data(), C.data(),
+                                             G.data(), step.data(), done.data(), red.data(), (zc*)out + k * (size_t)(d * n), &en);
+    energy[k] = en;
+  }
+  return 0;
+}
+
+int emu_gauge_back(int d, int D, int64_t N, const double* b, const double* x, const double* scale, double* out) {
+  const Grp g = solo();
+  const int n = D * D;
+  std::vector<zc> sB((size_t)d * n), sX(n), sXi(n), sT(n);
+  for (int64_t k = 0; k < N; ++k)
+    gauge_back_problem<double>(g, (const zc*)b + k * (size_t)(d * n), (const zc*)x + k * (size_t)n, scale[k], d, D, sB.data(), sX.data(),
+                               sXi.data(), sT.data(), (zc*)out + k * (size_t)(d * n));
   return 0;
 }
 

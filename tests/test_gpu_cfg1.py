@@ -225,3 +225,86 @@ def test_argmin_allreduce_single_rank_and_own_communicator(env):
     empty = t.empty((0,), dtype=t.float64, device="cuda")
     bc3, bi3 = dist.argmin_allreduce(empty)
     assert int(bi3.item()) == -1
+
+
+# ---------------------------------------------------------------- classical iTDVP
+@pytest.mark.parametrize("d,D,N", [(2, 2, 9), (2, 4, 7), (2, 5, 5), (2, 8, 4), (2, 10, 3), (2, 16, 2), (3, 3, 4)])
+def test_tdvp_tangent_vs_oracle(env, d, D, N):
+    """`iMPS.dA_dt` on the GPU against oracle/tdvp.py, bond dimensions of the reference's scripts included
+    (D = 5: qmps/loschmidts/mps_loschmidts.py:13, D = 10: scripts/classical_time_evolution.py:15): tensors in a
+    general gauge, the left-canonical fast entry, the imaginary-time variant and complex64."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    rng = np.random.default_rng(1000 * d + D)
+    A = rng.normal(size=(N, d, D, D)) + 1j * rng.normal(size=(N, d, D, D))
+    hm = rng.normal(size=(d * d, d * d)) + 1j * rng.normal(size=(d * d, d * d))
+    hm = hm + hm.conj().T
+    dA, e, st = B.tdvp_dadt(t.from_numpy(A).cuda(), hm, want_status=True)
+    assert int(st.abs().sum()) == 0
+    dA, e = dA.cpu().numpy(), e.cpu().numpy()
+    for k in range(N):
+        dA0, e0 = O.dA_dt(A[k], hm)
+        scale = max(1.0, np.abs(dA0).max())
+        assert np.abs(dA[k] - dA0).max() < 1e-8 * scale and abs(e[k] - e0) < 1e-9 * max(1.0, abs(e0))
+    AL = np.stack([O.tdvp_canonical_parts(a)[0] for a in A])
+    for imag in (False, True):
+        dL, eL = B.tdvp_dadt(t.from_numpy(AL).cuda(), hm, imaginary=imag, assume_left_canonical=True)
+        for k in range(N):
+            d0, e0 = O.tdvp_tangent_left_canonical(AL[k], hm, imaginary=imag)
+            assert np.abs(dL[k].cpu().numpy() - d0).max() < 1e-8 * max(1.0, np.abs(d0).max())
+    d32, _ = B.tdvp_dadt(t.from_numpy(AL).cuda().to(t.complex64), hm, assume_left_canonical=True)
+    ref = np.stack([O.tdvp_tangent_left_canonical(a, hm)[0] for a in AL])
+    assert np.abs(d32.cpu().numpy() - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_tdvp_rk4_and_euler_trajectories_vs_oracle(env):
+    """`qmps_tdvp_evolve` (whole trajectory on the device) against the oracle's step-by-step loop -- the
+    reference's RK4 body (scripts/classical_time_evolution.py:22-26) and Euler (mps_loschmidts.py:22)."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    h = O.tfim_matrix(0.7)
+    A = np.stack([O.unitary_to_tensor(unitary_group.rvs(2 * 4, random_state=70 + k)) for k in range(3)])
+    for method, steps, dt in (("rk4", 12, 0.02), ("euler", 12, 0.005)):
+        run = B.tdvp_evolve(t.from_numpy(A).cuda(), h, dt, steps, method=method, want_traj=True)
+        assert int(run.status.abs().sum()) == 0
+        traj, rates, en = run.traj.cpu().numpy(), run.rates.cpu().numpy(), run.energy.cpu().numpy()
+        for k in range(3):
+            ref = O.tdvp_trajectory(A[k], h, dt, steps, method=method)
+            rr = O.loschmidt_rates(ref)
+            for s in range(steps + 1):
+                assert abs(O.overlap(traj[s, k], ref[s]) - 1) < 1e-9            # same state (gauge-invariant)
+                assert abs(rates[s, k] - rr[s]) < 1e-9
+            assert abs(en[0, k] - O.energy_density(ref[0], h)) < 1e-10
+            if method == "rk4":
+                assert np.ptp(en[:, k]) < 1e-6                                   # energy conservation
+        assert t.equal(run.A, run.traj[-1])
+
+
+def test_tdvp_quench_rate_follows_exact_tfim_curve_on_gpu(env, golden):
+    """The experiment of qmps/loschmidts/mps_loschmidts.py on the device: imaginary-time TDVP to the ground state of
+    H(g0 = 1.5) at D = 5 (the script's D), quench to g1 = 0.2, RK4, `loschmidts()` against the analytic rate function
+    (qmps/loschmidts/exact_loschmidt.py) and against the reference's own recorded values of that function."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    from qmps_b200.imps import iMPS, Trajectory
+    g0, g1 = 1.5, 0.2
+    A = np.random.default_rng(0).normal(size=(1, 2, 5, 5)) + 0j
+    gs = B.tdvp_evolve(t.from_numpy(A).cuda(), O.tfim_matrix(g0), 0.05, 800, method="euler", imaginary=True, want_rates=False)
+    assert abs(gs.energy[-1, 0].item() - O.tfim_e0_exact(g0)) < 1e-4
+    T = np.linspace(0, 0.5, 51)
+    traj = Trajectory(mps_0=iMPS([gs.A[0].cpu().numpy()]), H=[O.tfim_matrix(g1)]).rk4int(T)
+    ls = traj.loschmidts()
+    assert ls[0] < 1e-10
+    for k in (10, 25, 50):
+        exact = float(O.exact_loschmidt(T[k], g0, g1))
+        assert abs(ls[k] - exact) < 0.01 * exact
+    ref = golden["ref_exact_loschmidt"]
+    kk = int(np.argmin(np.abs(ref["t"] - 0.5)))
+    assert abs(ls[50] - ref["g15_02"][kk]) < 0.01 * ref["g15_02"][kk]
+    # the reference's RK4 loop, verbatim, on the drop-in iMPS (scripts/classical_time_evolution.py:21-27)
+    mps = iMPS([gs.A[0].cpu().numpy()])
+    H = O.tfim_matrix(g1); dt = T[1] - T[0]
+    for _ in range(3):
+        k1 = mps.dA_dt([H]) * dt
+        k2 = (mps + k1 / 2).dA_dt([H]) * dt
+        k3 = (mps + k2 / 2).dA_dt([H]) * dt
+        k4 = (mps + k3).dA_dt([H]) * dt
+        mps = (mps + (k1 + 2 * k2 + 2 * k3 + k4) / 6).left_canonicalise()
+    assert abs(mps.overlap(traj.mps_list()[3]) - 1) < 1e-9

@@ -411,7 +411,7 @@ def test_c_abi_argument_validation_without_a_device(built):
     lib = L.load()
     ERR_ARG, ERR_UNSUPPORTED = -1, -3
     cases = [
-        (lib.qmps_fixed_point(2, 3, 1, 1, 1, 1, 0, 0, None, None, None, None, None, None, L.C128, None), ERR_UNSUPPORTED, "D must be"),
+        (lib.qmps_fixed_point(2, 17, 1, 1, 1, 1, 0, 0, None, None, None, None, None, None, L.C128, None), ERR_UNSUPPORTED, "D must be"),
         (lib.qmps_fixed_point(2, 2, 2, 1, 3, 1, 0, 0, None, None, None, None, None, None, L.C128, None), ERR_ARG, "broadcast"),
         (lib.qmps_fixed_point(2, 2, 1, 1, 1, 1, 0, 0, None, None, None, None, None, None, 7, None), ERR_ARG, "dtype"),
         (lib.qmps_tm_power(2, 4, 1, None, None, None, 1, None, L.C128, None), ERR_ARG, "tm_power"),
