@@ -314,6 +314,20 @@ int qmps_energy_theta_host(const qmps_gate_op* ops, int nops, int nq, int64_t N,
 int qmps_rotosolve_sweep(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, double* theta, const void* hmat,
                          int n_sweeps, int two_frequency, void* energy, int dtype, void* stream);
 
+/* (f)-2 the reference's time-evolution loop on the device (scripts/loschmidt.py:367-375 = qmps/loschmidts/time_evo.py:140-150):
+ *     theta_traj[0] = theta0; for each of n_steps steps  theta_traj[t+1] = argmin_p obj(p, A(theta_traj[t]), W)  with
+ *     obj(p, A, W) = -sqrt|eta(Map(W . merge(A,A), merge(B_p,B_p)))| (qmps/loschmidts/time_evo.py:75-116).  The reference
+ *     calls scipy.optimize.minimize per step; here each step is n_gen generations of a population search -- npop candidate
+ *     vectors per generation evaluated by ONE qmps_loschmidt_batched call, the argmin fed back on the device, step size
+ *     adapted from sigma0 -- followed by n_bfgs iterations of BFGS (what scipy's default minimiser does) whose
+ *     finite-difference gradient (2 P + 1 points) and line search (24 step sizes) are one launch each; no host round
+ *     trip anywhere.  n_gen = 0 starts BFGS from theta_t itself.  P <= 64.  Outputs (DEVICE): theta_traj [(n_steps+1)][P] doubles,
+ *     step_cost [n_steps] (the minimum found per step; 1 + step_cost is the projection error), echo [n_steps+1] =
+ *     |eta(E_{A_t A_0})|^2 (``A_.overlap(A)``; the reference plots -log of it against exact_loschmidt). */
+int qmps_loschmidt_trajectory(const qmps_gate_op* ops, int nops, int nq, int P, const double* theta0, const void* W,
+                              int n_steps, int n_gen, int npop, double sigma0, uint64_t seed, int n_bfgs, double* theta_traj,
+                              void* step_cost, void* echo, int dtype, void* stream);
+
 /* (e)  the final cost reduction across ranks: local argmin, one ncclAllGather of 16 bytes per
  *     rank and a final pass, all on `stream`; best_cost [1] / best_index [1] are DEVICE scalars, identical on
  *     every rank (ties: smallest global index; an empty shard contributes nothing).  `comm` is an ncclComm_t --

@@ -55,6 +55,7 @@ SIGNATURES = {
     "qmps_tdvp_tangent": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_tdvp_dadt": ([_i, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_tdvp_evolve": ([_i, _i, _i64, _vp, _vp, ctypes.c_double, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "qmps_loschmidt_trajectory": ([_gp, _i, _i, _i, _vp, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint64, _i, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_merge": ([_i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp], _i),
     "qmps_ansatz": ([_gp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp], _i),
     "qmps_energy_theta": ([_gp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp], _i),

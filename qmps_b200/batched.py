@@ -468,6 +468,32 @@ def tm_power(A, B, K, r0=None):
     return r, ray
 
 
+
+LoschmidtTrajectory = namedtuple("LoschmidtTrajectory", "theta step_cost echo")
+
+
+def loschmidt_trajectory(program, theta0, W, n_steps, n_gen=8, npop=2048, sigma0=0.05, seed=0, n_bfgs=30, dtype=torch.complex128):
+    """The reference's time-evolution loop (scripts/loschmidt.py:367-375) on the device in ONE C-ABI call
+    (``qmps_loschmidt_trajectory``): theta_{t+1} = argmin_p obj(p, A(theta_t), W) by ``n_gen`` generations of a
+    population search followed by ``n_bfgs`` BFGS iterations (batched finite-difference gradient and line search),
+    everything fed back on the device, then the echo series |eta(E_{A_t A_0})|^2.
+    Returns ``LoschmidtTrajectory(theta[n_steps+1, P], step_cost[n_steps], echo[n_steps+1])`` (CUDA tensors)."""
+    theta0 = _rdev(torch.as_tensor(np.asarray(theta0, dtype=np.float64)) if not isinstance(theta0, torch.Tensor) else theta0).reshape(-1).contiguous()
+    P = theta0.numel()
+    dev = theta0.device
+    Wd = _cdev(W, dtype, dev).reshape(4, 4).contiguous()
+    rd = _RDT[dtype]
+    traj = torch.empty((n_steps + 1, P), dtype=torch.float64, device=dev)
+    cost = torch.empty((n_steps,), dtype=rd, device=dev)
+    echo = torch.empty((n_steps + 1,), dtype=rd, device=dev)
+    ops = program.c_ops()
+    with torch.cuda.device(dev):
+        L.check(L.load().qmps_loschmidt_trajectory(ops, len(program), program.nq, P, _p(theta0), _p(Wd), int(n_steps), int(n_gen),
+                                                   int(npop), float(sigma0), int(seed), int(n_bfgs), _p(traj), _p(cost), _p(echo), _CDT[dtype],
+                                                   _stream()), "loschmidt_trajectory")
+    return LoschmidtTrajectory(traj, cost, echo)
+
+
 # ---- SURVEY 8(f)-3: classical iTDVP ------------------------------------------------------------
 def tdvp_dadt(A, h, imaginary=False, assume_left_canonical=False, want_status=False):
     """``iMPS([A]).dA_dt([h])`` for a batch A[N, d, D, D] (xmps; call sites scripts/classical_time_evolution.py:22-26,

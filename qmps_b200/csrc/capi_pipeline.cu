@@ -93,6 +93,136 @@ __global__ void pack_pair_kernel(const double* c, const long long* i, long long*
   if (threadIdx.x == 0 && blockIdx.x == 0) { pair[0] = __double_as_longlong(*c); pair[1] = *i; }
 }
 
+// ---- device-resident evolution strategy for the TDVP-step optimisation -----------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {        // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// candidates of one generation: row 0 is the centre itself, row c >= 1 is centre + sigma * 10^(-(c mod 4)/2) * normal
+__global__ void es_propose_kernel(int npop, int P, const double* __restrict__ centre, const double* __restrict__ sigma,
+                                  unsigned long long seed, unsigned long long gen, double* __restrict__ cand) {
+  const double sg = *sigma;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < npop * P; e += gridDim.x * blockDim.x) {
+    const int c = e / P, j = e - c * P;
+    double v = centre[j];
+    if (c > 0) {
+      const unsigned long long h1 = mix64(seed ^ mix64(gen * 0x100000001B3ull + (unsigned long long)e));
+      const unsigned long long h2 = mix64(h1 ^ 0xD6E8FEB86659FD93ull);
+      const double u1 = ((double)(h1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+      const double u2 = ((double)(h2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+      const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+      const int grp = c & 3;
+      const double sc = grp == 0 ? 1.0 : grp == 1 ? 0.316227766016838 : grp == 2 ? 0.1 : 0.0316227766016838;
+      v += sg * sc * z;
+    }
+    cand[e] = v;
+  }
+}
+// the winner becomes the centre; the step size follows the scale that won (halved when nothing beat the centre)
+__global__ void es_select_kernel(int P, const double* __restrict__ cand, const long long* __restrict__ best_index,
+                                 const double* __restrict__ best_cost, double* __restrict__ centre, double* __restrict__ sigma,
+                                 double* __restrict__ cost_out) {
+  const long long bi = *best_index;
+  for (int j = threadIdx.x; j < P; j += blockDim.x) centre[j] = cand[bi * P + j];
+  if (threadIdx.x == 0) {
+    const int grp = (int)(bi & 3);
+    const double sc = grp == 0 ? 1.0 : grp == 1 ? 0.316227766016838 : grp == 2 ? 0.1 : 0.0316227766016838;
+    double sg = *sigma;
+    sg = bi == 0 ? sg * 0.5 : sg * sc * 2.0;
+    if (sg < 1e-9) sg = 1e-9;
+    if (sg > 1.0) sg = 1.0;
+    *sigma = sg;
+    if (cost_out) *cost_out = *best_cost;
+  }
+}
+// ---- device-resident BFGS with batched finite-difference gradients and a batched line search ----------------
+// (what scipy.optimize.minimize's default does for the reference, scripts/loschmidt.py:371, with every cost
+// evaluation of an iteration issued as ONE launch and no value ever leaving the device)
+constexpr int BFGS_LS = 24;                 // line-search step sizes 2, 1, 1/2, ..., 2^-22
+__global__ void bfgs_probe_kernel(int P, const double* __restrict__ theta, double h, double* __restrict__ cand) {
+  for (int e = threadIdx.x; e < (2 * P + 1) * P; e += blockDim.x) {
+    const int c = e / P, j = e - c * P;
+    double v = theta[j];
+    if (c >= 1 && c <= P && c - 1 == j) v += h;
+    if (c > P && c - P - 1 == j) v -= h;
+    cand[e] = v;
+  }
+}
+// state: g[P], gprev[P], s[P], d[P], H[P*P], f0, have_prev.  One CTA of 64 threads, P <= 64.
+__global__ void bfgs_direction_kernel(int P, const double* __restrict__ costs, double h, double* g, double* gprev, double* s,
+                                      double* d, double* H, double* f0, int* have_prev, double* __restrict__ theta,
+                                      double* __restrict__ cand) {
+  __shared__ double sh_y[64], sh_Hy[64], sh_red[64];
+  const int j = threadIdx.x;
+  if (j < P) g[j] = (costs[1 + j] - costs[1 + P + j]) / (2.0 * h);
+  if (j == 0) *f0 = costs[0];
+  __syncthreads();
+  if (*have_prev) {
+    // BFGS update of the inverse Hessian with s = last step, y = g - gprev (skipped unless y.s > 0)
+    if (j < P) sh_y[j] = g[j] - gprev[j];
+    __syncthreads();
+    double ys = 0.0, ss = 0.0;
+    for (int k = 0; k < P; ++k) { ys += sh_y[k] * s[k]; ss += s[k] * s[k]; }
+    if (ys > 1e-300 && ss > 0.0 && ys > 1e-12 * sqrt(ss)) {
+      if (j < P) { double a = 0.0; for (int k = 0; k < P; ++k) a += H[j * P + k] * sh_y[k]; sh_Hy[j] = a; }
+      __syncthreads();
+      double yHy = 0.0;
+      for (int k = 0; k < P; ++k) yHy += sh_y[k] * sh_Hy[k];
+      const double rho = 1.0 / ys;
+      if (j < P)
+        for (int k = 0; k < P; ++k)
+          H[j * P + k] += -rho * (sh_Hy[j] * s[k] + s[j] * sh_Hy[k]) + rho * rho * yHy * s[j] * s[k] + rho * s[j] * s[k];
+    }
+    __syncthreads();
+  } else {                                   // first iteration, or the last line search failed: steepest descent restart
+    if (j < P) for (int k = 0; k < P; ++k) H[j * P + k] = (j == k) ? 1.0 : 0.0;
+    __syncthreads();
+  }
+  if (j < P) { double a = 0.0; for (int k = 0; k < P; ++k) a += H[j * P + k] * g[k]; d[j] = -a; }
+  __syncthreads();
+  if (j < P) sh_red[j] = d[j] * g[j];
+  __syncthreads();
+  double dg = 0.0;
+  for (int k = 0; k < P; ++k) dg += sh_red[k];
+  if (!(dg < 0.0)) {                         // not a descent direction: restart from steepest descent
+    __syncthreads();
+    if (j < P) { for (int k = 0; k < P; ++k) H[j * P + k] = (j == k) ? 1.0 : 0.0; d[j] = -g[j]; }
+  }
+  __syncthreads();
+  if (j < P) gprev[j] = g[j];
+  // line-search candidates theta + alpha_l d
+  for (int e = threadIdx.x; e < BFGS_LS * P; e += blockDim.x) {
+    const int l = e / P, k = e - l * P;
+    cand[e] = theta[k] + ldexp(2.0, -l) * d[k];
+  }
+}
+__global__ void bfgs_step_kernel(int P, const double* __restrict__ costs, const double* __restrict__ d, double* s, const double* f0,
+                                 int* have_prev, double* __restrict__ theta, double* __restrict__ fbest) {
+  __shared__ int best_l;
+  if (threadIdx.x == 0) {
+    int bl = -1; double bc = *f0;
+    for (int l = 0; l < BFGS_LS; ++l) if (costs[l] < bc) { bc = costs[l]; bl = l; }
+    best_l = bl;
+    *fbest = bc;
+    *have_prev = bl >= 0;                    // no progress: the next direction restarts without an update
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j < P) {
+    const double step = best_l >= 0 ? ldexp(2.0, -best_l) * d[j] : 0.0;
+    s[j] = step;
+    theta[j] += step;
+  }
+}
+__global__ void bfgs_init_kernel(int P, double* H, int* have_prev) {
+  for (int e = threadIdx.x; e < P * P; e += blockDim.x) H[e] = (e / P == e % P) ? 1.0 : 0.0;
+  if (threadIdx.x == 0) *have_prev = 0;
+}
+__global__ void narrow_kernel(const double* in, float* out) { if (threadIdx.x == 0 && blockIdx.x == 0) *out = (float)*in; }
+__global__ void set_scalar_kernel(double* p, double v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
 }  // namespace
 
 extern "C" {
@@ -207,6 +337,82 @@ int qmps_rotosolve_sweep(const qmps_gate_op* ops, int nops, int nq, int64_t N, i
     }
   }
   if (energy) return qmps_energy_theta(ops, nops, nq, N, P, theta, hmat, -1, nullptr, 0, energy, nullptr, dtype, stream);
+  return 0;
+}
+
+// (f)-2: the reference's time-evolution loop (scripts/loschmidt.py:367-375 = qmps/loschmidts/time_evo.py:140-150)
+// on the device, no host round trip: for each step  theta <- argmin_p obj(p, A(theta), W)  with
+// obj = -sqrt|eta(Map(W . merge(A,A), merge(B_p,B_p)))|, minimised by a population search (npop candidates per
+// generation in ONE qmps_loschmidt_batched call, the argmin fed back on the device), then the echo series
+// |eta(E_{A_t A_0})|^2 (``A_.overlap(A)``) for the whole trajectory.
+int qmps_loschmidt_trajectory(const qmps_gate_op* ops, int nops, int nq, int P, const double* theta0, const void* W,
+                              int n_steps, int n_gen, int npop, double sigma0, uint64_t seed, int n_bfgs, double* theta_traj,
+                              void* step_cost, void* echo, int dtype, void* stream) {
+  if (!ops || nq < 2 || nq > 5 || P < 1 || P > 64 || !theta0 || !W || n_steps < 0 || n_gen < 0 || n_bfgs < 0 || (n_gen && (npop < 8 || !(sigma0 > 0))) || !theta_traj)
+    return fail(QMPS_ERR_ARG, "loschmidt_trajectory: bad arguments");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "loschmidt_trajectory: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = 1 << (nq - 1);
+  const size_t cs = csize(dtype), rs = rsize(dtype);
+  Scratch scratch(st);
+  double *cand = nullptr, *sigma = nullptr, *bc = nullptr; long long* bi = nullptr; char *At = nullptr, *cost = nullptr, *Aall = nullptr;
+  double* cost64 = nullptr;
+  const int ncand = npop > 2 * P + 1 ? (npop > BFGS_LS ? npop : BFGS_LS) : (2 * P + 1 > BFGS_LS ? 2 * P + 1 : BFGS_LS);
+  double *bg = nullptr, *bgp = nullptr, *bs = nullptr, *bd = nullptr, *bH = nullptr, *bf0 = nullptr; int* bhave = nullptr;
+  CK(scratch.get(&bg, sizeof(double) * P)); CK(scratch.get(&bgp, sizeof(double) * P)); CK(scratch.get(&bs, sizeof(double) * P));
+  CK(scratch.get(&bd, sizeof(double) * P)); CK(scratch.get(&bH, sizeof(double) * P * P)); CK(scratch.get(&bf0, sizeof(double)));
+  CK(scratch.get(&bhave, sizeof(int)));
+  CK(scratch.get(&cand, sizeof(double) * (size_t)ncand * P));
+  CK(scratch.get(&sigma, sizeof(double)));
+  CK(scratch.get(&bc, sizeof(double)));
+  CK(scratch.get(&bi, sizeof(long long)));
+  CK(scratch.get(&At, cs * 2 * D * D));
+  CK(scratch.get(&cost, rs * ncand));
+  if (dtype != QMPS_C128) CK(scratch.get(&cost64, sizeof(double) * ncand));
+  CK(cudaMemcpyAsync(theta_traj, theta0, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+  const int pg = (npop * P + 255) / 256;
+  for (int step = 0; step < n_steps; ++step) {
+    double* centre = theta_traj + (size_t)(step + 1) * P;
+    CK(cudaMemcpyAsync(centre, theta_traj + (size_t)step * P, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+    if (int rc = qmps_ansatz(ops, nops, nq, 1, P, theta_traj + (size_t)step * P, 0, At, dtype, stream)) return rc;      // A_t
+    set_scalar_kernel<<<1, 32, 0, st>>>(sigma, sigma0);
+    for (int gen = 0; gen < n_gen; ++gen) {
+      es_propose_kernel<<<pg, 256, 0, st>>>(npop, P, centre, sigma, (unsigned long long)seed,
+                                            (unsigned long long)step * (unsigned long long)n_gen + gen, cand);
+      if (int rc = qmps_loschmidt_batched(ops, nops, nq, npop, P, cand, At, 1, W, cost, nullptr, nullptr, nullptr, dtype, stream)) return rc;
+      const double* c64 = (const double*)cost;
+      if (dtype != QMPS_C128) { widen_kernel<<<(npop + 255) / 256, 256, 0, st>>>(npop, (const float*)cost, cost64); c64 = cost64; }
+      if (int rc = qmps_argmin(npop, c64, 0, bc, (int64_t*)bi, stream)) return rc;
+      es_select_kernel<<<1, 64, 0, st>>>(P, cand, bi, bc, centre, sigma, nullptr);
+    }
+    // BFGS refinement from the population's best point (or from theta_t when n_gen = 0)
+    auto evaluate = [&](int n) -> int {
+      if (int rc = qmps_loschmidt_batched(ops, nops, nq, n, P, cand, At, 1, W, cost, nullptr, nullptr, nullptr, dtype, stream)) return rc;
+      if (dtype != QMPS_C128) widen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const float*)cost, cost64);
+      return 0;
+    };
+    const double* c64 = dtype == QMPS_C128 ? (const double*)cost : cost64;
+    const double hfd = dtype == QMPS_C128 ? 1e-5 : 3e-3;
+    if (n_bfgs > 0) bfgs_init_kernel<<<1, 64, 0, st>>>(P, bH, bhave);
+    for (int it = 0; it < n_bfgs; ++it) {
+      bfgs_probe_kernel<<<1, 256, 0, st>>>(P, centre, hfd, cand);
+      if (int rc = evaluate(2 * P + 1)) return rc;
+      bfgs_direction_kernel<<<1, 64, 0, st>>>(P, c64, hfd, bg, bgp, bs, bd, bH, bf0, bhave, centre, cand);
+      if (int rc = evaluate(BFGS_LS)) return rc;
+      bfgs_step_kernel<<<1, 64, 0, st>>>(P, c64, bd, bs, bf0, bhave, centre, bc);
+    }
+    if (step_cost) {
+      if (dtype == QMPS_C128) CK(cudaMemcpyAsync((double*)step_cost + step, bc, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      else narrow_kernel<<<1, 32, 0, st>>>(bc, (float*)step_cost + step);
+    }
+  }
+  if (echo) {
+    const int64_t NT = (int64_t)n_steps + 1;
+    CK(scratch.get(&Aall, cs * NT * 2 * D * D));
+    if (int rc = qmps_ansatz(ops, nops, nq, NT, P, theta_traj, 0, Aall, dtype, stream)) return rc;
+    if (int rc = qmps_fixed_point(2, D, NT, Aall, 1, Aall, 0, 0, nullptr, nullptr, nullptr, nullptr, echo, nullptr, dtype, stream)) return rc;
+  }
+  CK(cudaGetLastError());
   return 0;
 }
 
