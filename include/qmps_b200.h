@@ -200,6 +200,15 @@ int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r
 int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, const void* Y,
                       int conj_y, void* C, void* stream);
 
+/* the complex128 counterpart on tcgen05 kind::i8: C[b] = X[b] . Y[b]^T (conj_y = 0) or X[b] . Y[b]^H (1) with
+ *     X [batch][M][K], Y [batch][N][K], C [batch][M][N] complex128, M % 64 == 0, N % 32 == 0, K % 64 == 0.
+ *     Every real operand row is cut into six signed 7-bit slices under a power-of-two row scale; the 21 slice
+ *     products with i + j < 6 are exact int32 tensor-core products, recombined in FP64 (relative error ~4e-12).
+ *     qmps_tm_power uses it for complex128 when D % 64 == 0 (option "i8_power"). */
+int qmps_zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C,
+                       void* stream);
+
+
 /* ---- canonical forms and local expectation values (xmps' iMPS methods as the
  *      reference's loops call them; xmps is not vendored, so the gauge is this build's documented
  *      Cholesky gauge -- every quantity the call sites consume is gauge invariant) ---------------- */

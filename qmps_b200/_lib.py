@@ -62,6 +62,7 @@ SIGNATURES = {
     "qmps_energy_tensor": ([_i, _i64, _vp, _i, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_rotosolve_fit": ([_i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "qmps_tm_power": ([_i, _i, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp], _i),
+    "qmps_zgemm_c128_i8": ([_i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
     "qmps_cgemm_c64_tc": ([_i64, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
     "qmps_left_canonicalise": ([_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_mixed_canonical": ([_i, _i, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),

@@ -531,6 +531,20 @@ def tdvp_evolve(A, h, dt, n_steps, method="rk4", imaginary=False, want_traj=Fals
     return TdvpRun(A, traj, rates, en, st)
 
 
+
+def zgemm_i8(X, Y, conj_y=False):
+    """C[b] = X[b] . Y[b]^T (or ^H) in complex128 on tcgen05 kind::i8 (exact int8 slice products, FP64 recombination):
+    X[batch, M, K], Y[batch, N, K] -> C[batch, M, N]; M % 64 == 0, N % 32 == 0, K % 64 == 0 (``qmps_zgemm_c128_i8``)."""
+    X = _cdev(X, torch.complex128)
+    Y = _cdev(Y, torch.complex128, X.device)
+    batch, M, K = X.shape
+    N = Y.shape[1]
+    C = torch.empty((batch, M, N), dtype=torch.complex128, device=X.device)
+    with torch.cuda.device(X.device):
+        L.check(L.load().qmps_zgemm_c128_i8(batch, M, N, K, _p(X), _p(Y), int(bool(conj_y)), _p(C), _stream()), "zgemm_c128_i8")
+    return C
+
+
 # ---- (e) -----------------------------------------------------------------------------
 def argmin(cost, index_offset=0):
     """(min, argmin + index_offset) of a float64 CUDA vector, as 1-element CUDA tensors."""

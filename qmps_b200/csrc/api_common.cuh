@@ -23,7 +23,7 @@ inline int fail(int code, const std::string& msg) { last_error() = msg; return c
   } while (0)
 
 // tuning knobs (qmps_set_option); defaults are the measured best
-enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_TC_POWER = 4, OPT_TC_PERSISTENT = 5, OPT_FP_GROUP = 6, OPT_FP_BLOCK = 7, OPT_ER_WIDE = 8, OPT_FP_D2 = 9, OPT_BW_THREAD = 10, OPT_COUNT = 11 };
+enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_TC_POWER = 4, OPT_TC_PERSISTENT = 5, OPT_FP_GROUP = 6, OPT_FP_BLOCK = 7, OPT_ER_WIDE = 8, OPT_FP_D2 = 9, OPT_BW_THREAD = 10, OPT_I8_POWER = 11, OPT_COUNT = 12 };
 int option_get(int key);                          // defined in capi.cu
 
 inline int sm_count() {
@@ -147,6 +147,11 @@ int fixed_point_f32(const qmps::FpParams& p, cudaStream_t st);
 int fp16_debug_f64(unsigned long long* out, int reset);
 int ansatz_f64(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
 int ansatz_f32(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
+// capi_tc_i8.cu
+bool i8_shape_ok(int M, int N, int K);
+int zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C, cudaStream_t st);
+bool tm_power_i8_applies(int d, int D, int64_t N);
+int tm_power_i8(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K, void* rayleigh, cudaStream_t st);
 // capi_d2.cu
 int env_d2(int64_t N, const void* in, int in_is_U, void* eta, void* r, void* C, int32_t* status, int dtype, cudaStream_t st);
 int energy_d2_theta(const qmps::GateOp* dops, int nops, int64_t N, int P, const double* theta, const void* hmat, int coord,

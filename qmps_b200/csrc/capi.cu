@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 7 /* fp16_fast: D = 4 eigenvalue-only kernel; 0 generic, 1/2 half-warp registers, 3-5 quarter-warp registers, 6 shared-resident, 7 shared-resident quarter-warp (measured best: profiles/exp_fp16_r02f.jsonl) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 7 /* fp16_fast: D = 4 eigenvalue-only kernel; 0 generic, 1/2 half-warp registers, 3-5 quarter-warp registers, 6 shared-resident, 7 shared-resident quarter-warp (measured best: profiles/exp_fp16_r02f.jsonl) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */, 1 /* i8_power: complex128 D % 64 == 0 on tcgen05 kind::i8 */};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
@@ -115,6 +115,7 @@ int qmps_set_option(const char* name, int value) {
   if (!strcmp(name, "d2_pdl")) { g_options[OPT_D2_PDL] = value; return 0; }
   if (!strcmp(name, "d2_ctas_per_sm")) { g_options[OPT_D2_CTAS_PER_SM] = value; return 0; }
   if (!strcmp(name, "fp16_fast")) { g_options[OPT_FP16_FAST] = value; return 0; }
+  if (!strcmp(name, "i8_power")) { g_options[OPT_I8_POWER] = value; return 0; }
   if (!strcmp(name, "env_real")) { g_options[OPT_ENV_REAL] = value; return 0; }
   if (!strcmp(name, "tc_power")) { g_options[OPT_TC_POWER] = value; return 0; }
   if (!strcmp(name, "tc_persistent")) { g_options[OPT_TC_PERSISTENT] = value; return 0; }
@@ -339,7 +340,8 @@ int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r
     char* r = (char*)r_io + csz * (size_t)n0 * DD;
     void* ray = rayleigh ? (void*)((char*)rayleigh + csz * (size_t)n0) : nullptr;
     int rc;
-    if (dtype == QMPS_C128) rc = tm_power_f64(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
+    if (dtype == QMPS_C128 && tm_power_i8_applies(d, D, n)) rc = tm_power_i8(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
+    else if (dtype == QMPS_C128) rc = tm_power_f64(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
     else if (tm_power_tc_applies(d, D, n)) rc = tm_power_tc(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
     else rc = tm_power_impl<float>(d, D, n, a, b, r, K, ray, (cudaStream_t)stream);
     if (rc) return rc;
@@ -351,6 +353,11 @@ int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* 
                       void* stream) {
   if (batch < 0 || nsum < 1 || (batch && (!X || !Y || !C))) return fail(QMPS_ERR_ARG, "cgemm_c64_tc: bad arguments");
   return cgemm_c64_tc(batch, nsum, M, N, K, X, Y, conj_y, C, (cudaStream_t)stream);
+}
+
+int qmps_zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C, void* stream) {
+  if (batch < 0 || (batch && (!X || !Y || !C))) return fail(QMPS_ERR_ARG, "zgemm_c128_i8: bad arguments");
+  return zgemm_c128_i8(batch, M, N, K, X, Y, conj_y, C, (cudaStream_t)stream);
 }
 
 int qmps_argmin(int64_t N, const double* cost, int64_t index_offset, double* best_cost, int64_t* best_index,

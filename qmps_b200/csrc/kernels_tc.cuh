@@ -70,7 +70,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // ---- pack: interleaved complex64 matrices -> slab images --------------------------------------
 // element (row, k) of matrix m is in[m * mstride + row * rstride + k * kstride]
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 pack_kernel(int64_t nmat, int R, int K, const cx<float>* __restrict__ in, int64_t mstride, int64_t rstride,
             int64_t kstride, unsigned char* __restrict__ img) {
   const int nrb = R / ROWS, nkb = K / KS;
@@ -195,7 +195,7 @@ struct Params {
   cx<float>* dot_out;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+static __global__ void __launch_bounds__(THREADS, 1)
 cgemm_tc_kernel(Params p) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * NSTAGE + 4];
@@ -409,7 +409,7 @@ cgemm_tc_kernel(Params p) {
 }
 
 // r[b] *= 1/sqrt(sum_j norm[b*n + j])
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 scale_by_norm_kernel(int64_t len, cx<float>* __restrict__ r, const float* __restrict__ norm, int n) {
   float s = 0.0f;
   for (int j = 0; j < n; ++j) s += norm[(size_t)blockIdx.x * n + j];
@@ -418,7 +418,7 @@ scale_by_norm_kernel(int64_t len, cx<float>* __restrict__ r, const float* __rest
   for (int64_t i = threadIdx.x; i < len; i += blockDim.x) p[i] = p[i] * a;
 }
 // out[b] = sum_j part[b*n + j]
-__global__ void sum_partials_kernel(int64_t nb, const cx<float>* __restrict__ part, int n, cx<float>* __restrict__ out) {
+static __global__ void sum_partials_kernel(int64_t nb, const cx<float>* __restrict__ part, int n, cx<float>* __restrict__ out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   cx<float> s = mk<float>(0.f, 0.f);

@@ -1031,3 +1031,56 @@ def test_torch_library_ops_match_batched_api(env):
     W = t.from_numpy(haar_batch(16, 1, 72)[0]).cuda()
     c = t.ops.qmps_b200.bw_evolve_cost(U[0], U[1], U[2:], U[2:].flip(0).contiguous(), W)
     assert t.equal(c, BW.bw_evolve_cost(U[0], U[1], U[2:], U[2:].flip(0).contiguous(), W))
+
+
+# ---------------------------------------------------------------- complex128 on tcgen05 kind::i8
+@pytest.mark.parametrize("shape", [(1, 64, 32, 64, 0), (2, 64, 64, 128, 1), (3, 128, 96, 64, 0), (2, 256, 256, 256, 1), (1, 64, 32, 512, 1)])
+def test_zgemm_i8_vs_numpy(env, shape):
+    """The int8-slice complex128 product (kernels_tc_i8.cuh) against numpy: random matrices, rows of very
+    different magnitude (the per-row power-of-two scales), exact zeros, and a structured case."""
+    t, B = env["torch"], env["B"]
+    batch, M, N, K, conj = shape
+    rng = np.random.default_rng(M + N + K)
+    X = rng.normal(size=(batch, M, K)) + 1j * rng.normal(size=(batch, M, K))
+    Y = rng.normal(size=(batch, N, K)) + 1j * rng.normal(size=(batch, N, K))
+    X *= np.exp2(rng.integers(-30, 30, size=(batch, M, 1)))          # row scales over 18 orders of magnitude
+    Y *= np.exp2(rng.integers(-30, 30, size=(batch, N, 1)))
+    X[0, 3] = 0.0; Y[0, 5].imag = 0.0
+    C = B.zgemm_i8(X, Y, conj_y=bool(conj)).cpu().numpy()
+    ref = X @ (Y.conj() if conj else Y).transpose(0, 2, 1)
+    # error bound of the scheme: 2^-42 of |row|max |col|max K per entry; compare entrywise against that scale
+    scale = np.maximum(np.abs(X).max(axis=2)[:, :, None] * np.abs(Y).max(axis=2)[:, None, :] * K, 1e-300)
+    assert (np.abs(C - ref) / scale).max() < 1e-11
+    assert np.abs(C[0, 3]).max() == 0.0
+    # relative Frobenius error on well-scaled operands: the 4e-12 of the numpy prototype
+    X1 = rng.normal(size=(batch, M, K)) + 1j * rng.normal(size=(batch, M, K))
+    Y1 = rng.normal(size=(batch, N, K)) + 1j * rng.normal(size=(batch, N, K))
+    C1 = B.zgemm_i8(X1, Y1, conj_y=bool(conj)).cpu().numpy()
+    ref1 = X1 @ (Y1.conj() if conj else Y1).transpose(0, 2, 1)
+    assert np.linalg.norm(C1 - ref1) / np.linalg.norm(ref1) < 2e-11
+    # integers are reproduced exactly
+    Xi = rng.integers(-50, 50, size=(batch, M, K)) + 1j * rng.integers(-50, 50, size=(batch, M, K))
+    Yi = rng.integers(-50, 50, size=(batch, N, K)) + 1j * rng.integers(-50, 50, size=(batch, N, K))
+    Ci = B.zgemm_i8(Xi, Yi, conj_y=bool(conj)).cpu().numpy()
+    assert np.array_equal(Ci, Xi @ (Yi.conj() if conj else Yi).transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("D,cnt,K", [(64, 3, 8), (128, 2, 5), (256, 2, 8), (64, 2, 0), (64, 2, 1)])
+def test_tm_power_complex128_tcgen05_vs_oracle_and_dmma(env, D, cnt, K):
+    """complex128 power method on tcgen05 kind::i8 against the oracle doing the identical K steps (1e-10), and
+    against the FP64 tensor-pipe (DMMA) path it replaces."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    A, Bt = tensors(D, cnt, 4000 + D, O), tensors(D, cnt, 5000 + D, O)
+    lib = L.load()
+    r, ray = B.tm_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), K)
+    lib.qmps_set_option(b"i8_power", 0)
+    try:
+        r2, ray2 = B.tm_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), K)
+        t.cuda.synchronize()
+    finally:
+        lib.qmps_set_option(b"i8_power", 1)
+    r, ray, r2, ray2 = r.cpu().numpy(), ray.cpu().numpy(), r2.cpu().numpy(), ray2.cpu().numpy()
+    for k in range(cnt):
+        r0, q0 = O.power_method(A[k], Bt[k], K)
+        assert np.abs(r[k] - r0).max() < TOL and abs(ray[k] - q0) < TOL
+    assert np.abs(r - r2).max() < TOL and np.abs(ray - ray2).max() < TOL
