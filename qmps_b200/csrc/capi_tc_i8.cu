@@ -15,13 +15,15 @@ int64_t yimg_bytes(int64_t nmat, int R, int K) { return nmat * (int64_t)(R / tci
 int launch_slice(int64_t nmat, int R, int K, const Z* in, int64_t mstride, int64_t rstride, int kin, int64_t kstride,
                  int64_t kostride, int is_y, const double* norm_in, int n_in, int a_div, unsigned char* img, int* ex,
                  cudaStream_t st) {
-  const int64_t warps = nmat * R;
-  if (warps == 0) return 0;
+  if (nmat * R == 0) return 0;
+  int G = 1;
+  while (G < 32 && G * 2 <= K / 16) G *= 2;                 // lanes per row
+  const int64_t warps = (nmat * R + (32 / G) - 1) / (32 / G);
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   tci8::slice_kernel<<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kin, kstride, kostride, is_y, norm_in,
-                                                       n_in, a_div, img, ex);
+                                                       n_in, a_div, img, ex, G);
   CK(cudaGetLastError());
   return 0;
 }
@@ -95,7 +97,7 @@ int tm_power_i8(int d, int D, int64_t N, const void* A, const void* B, void* r_i
   Scratch scratch(st);
   unsigned char *Ai = nullptr, *Bi = nullptr, *Ti = nullptr, *Ri = nullptr;
   int *eA = nullptr, *eB = nullptr, *eT = nullptr, *eR = nullptr;
-  Z *Tb = nullptr, *Er = nullptr, *dots = nullptr; double* nrm = nullptr;
+  Z *Tb = nullptr, *Er = nullptr, *dots = nullptr, *Rt = nullptr; double* nrm = nullptr;
   CK(scratch.get(&Ai, ximg_bytes(N * d, D, D)));
   CK(scratch.get(&Bi, yimg_bytes(N, D, d * D)));
   CK(scratch.get(&Ti, ximg_bytes(N, D, d * D)));
@@ -106,13 +108,17 @@ int tm_power_i8(int d, int D, int64_t N, const void* A, const void* B, void* r_i
   CK(scratch.get(&eR, sizeof(int) * N * D * 2));
   CK(scratch.get(&Tb, sizeof(Z) * N * d * DD));
   CK(scratch.get(&nrm, sizeof(double) * N * tiles2));
+  CK(scratch.get(&Rt, sizeof(Z) * N * DD));
   Z* r = (Z*)r_io;
   // constant operands, sliced once: A_s[i][k] as X; B[b][l][(s, j)] = B_s[l][j] as Y
   if (int rc = launch_slice(N * d, D, D, (const Z*)A, DD, D, D, 1, 0, 0, nullptr, 0, 1, Ai, eA, st)) return rc;
   if (int rc = launch_slice(N, D, d * D, (const Z*)B, d * DD, D, D, 1, DD, 1, nullptr, 0, 1, Bi, eB, st)) return rc;
-  auto apply = [&](const Z* src, const double* norm_in, double* norm_out, Z* out_c, const Z* dot_with, Z* dot_out) -> int {
+  // src_t != nullptr: r is available transposed (rows j, K = k contiguous: coalesced slicing), else strided reads of src
+  auto apply = [&](const Z* src, const Z* src_t, const double* norm_in, double* norm_out, Z* out_c, Z* out_ct, const Z* dot_with,
+                   Z* dot_out) -> int {
     // r^T: rows j, K = k, element (j, k) = r[k][j]; the 1 / |r| of the previous application is folded into the slicing
-    if (int rc = launch_slice(N, D, D, src, DD, 1, D, D, 0, 1, norm_in, tiles2, 1, Ri, eR, st)) return rc;
+    if (src_t) { if (int rc = launch_slice(N, D, D, src_t, DD, D, D, 1, 0, 1, norm_in, tiles2, 1, Ri, eR, st)) return rc; }
+    else if (int rc = launch_slice(N, D, D, src, DD, 1, D, D, 0, 1, norm_in, tiles2, 1, Ri, eR, st)) return rc;
     tci8::Params p1;
     memset(&p1, 0, sizeof(p1));
     p1.X = Ai; p1.Y = Ri; p1.ex_x = eA; p1.ex_y = eR; p1.nkb = D / tci8::KS; p1.nrbX = D / tci8::XROWS; p1.ncbY = D / tci8::YROWS;
@@ -123,16 +129,16 @@ int tm_power_i8(int d, int D, int64_t N, const void* A, const void* B, void* r_i
     tci8::Params p2;
     memset(&p2, 0, sizeof(p2));
     p2.X = Ti; p2.Y = Bi; p2.ex_x = eT; p2.ex_y = eB; p2.nkb = d * D / tci8::KS; p2.nrbX = D / tci8::XROWS; p2.ncbY = D / tci8::YROWS;
-    p2.y_div = 1; p2.batch = (int)N; p2.conj_y = 1; p2.out_c = out_c; p2.norm_out = norm_out; p2.dot_with = dot_with; p2.dot_out = dot_out;
+    p2.y_div = 1; p2.batch = (int)N; p2.conj_y = 1; p2.out_c = out_c; p2.out_ct = out_ct; p2.norm_out = norm_out; p2.dot_with = dot_with; p2.dot_out = dot_out;
     return launch_tile(p2, st);
   };
   for (int it = 0; it < K; ++it)
-    if (int rc = apply(r, it == 0 ? nullptr : nrm, nrm, r, nullptr, nullptr)) return rc;
+    if (int rc = apply(r, it == 0 ? nullptr : Rt, it == 0 ? nullptr : nrm, nrm, it == K - 1 ? r : nullptr, Rt, nullptr, nullptr)) return rc;
   if (K > 0) i8_scale_kernel<<<(unsigned)N, 256, 0, st>>>(DD, r, nrm, tiles2);
   if (rayleigh) {
     CK(scratch.get(&Er, sizeof(Z) * N * DD));
     CK(scratch.get(&dots, sizeof(Z) * N * tiles2));
-    if (int rc = apply(r, nullptr, nullptr, Er, r, dots)) return rc;
+    if (int rc = apply(r, nullptr, nullptr, nullptr, Er, nullptr, r, dots)) return rc;
     i8_sum_partials_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, dots, tiles2, (Z*)rayleigh);
   }
   CK(cudaGetLastError());

@@ -61,14 +61,19 @@ QMPS_HD uint32_t img_off(int prow, int bcol) {
 static __global__ void __launch_bounds__(256)
 slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int64_t mstride, int64_t rstride, int kin,
              int64_t kstride, int64_t kostride, int is_y, const double* __restrict__ norm_in, int n_in, int a_div,
-             unsigned char* __restrict__ img, int* __restrict__ ex) {
-  const int lane = threadIdx.x & 31;
+             unsigned char* __restrict__ img, int* __restrict__ ex, int G) {
+  // G lanes per complex row (a power of two <= 32, <= K / 16): a K = 64 row keeps 4 lanes busy, so 8 rows share a warp
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), rpw = 32 / G;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int brows = is_y ? YROWS : XROWS;
-  const int nrb = R / brows, nkb = K / KS;
+  const int nrb = R / brows, nkb = K / KS, nchunk = K / 16;
   const int64_t slab = is_y ? Y_SLAB : X_SLAB, plane = is_y ? Y_PLANE : X_PLANE;
-  for (int64_t w = warp; w < nmat * R; w += nwarps) {
+  const int64_t nrows = nmat * R;
+  for (int64_t w0 = warp * rpw; w0 < nrows; w0 += nwarps * rpw) {
+    int64_t w = w0 + lane / G;
+    const bool live = w < nrows;
+    if (!live) w = nrows - 1;
     const int64_t m = w / R;
     const int row = (int)(w - m * R);
     double alpha = 1.0;
@@ -80,22 +85,25 @@ slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int6
     }
     const cx<double>* src = in + m * mstride + row * rstride;
     double mre = 0.0, mim = 0.0;
-    for (int k = lane; k < K; k += 32) {
-      const cx<double> z = src[(k / kin) * kostride + (k % kin) * kstride];
-      mre = fmax(mre, fabs(z.re)); mim = fmax(mim, fabs(z.im));
+    for (int c = gl; c < nchunk; c += G) {
+#pragma unroll 4
+      for (int t = 0; t < 16; ++t) {
+        const int k = c * 16 + t;
+        const cx<double> z = src[(k / kin) * kostride + (k % kin) * kstride];
+        mre = fmax(mre, fabs(z.re)); mim = fmax(mim, fabs(z.im));
+      }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = G >> 1; o > 0; o >>= 1) {
       mre = fmax(mre, __shfl_xor_sync(0xffffffffu, mre, o));
       mim = fmax(mim, __shfl_xor_sync(0xffffffffu, mim, o));
     }
     int ere = 0, eim = 0;
     if (mre * alpha > 0.0) { frexp(mre * alpha, &ere); ere += 1; }      // |x| / 2^e < 1/2
     if (mim * alpha > 0.0) { frexp(mim * alpha, &eim); eim += 1; }
-    if (lane == 0) { ex[(m * R + row) * 2] = ere; ex[(m * R + row) * 2 + 1] = eim; }
+    if (live && gl == 0) { ex[(m * R + row) * 2] = ere; ex[(m * R + row) * 2 + 1] = eim; }
     const double sre = ldexp(alpha, -ere), sim = ldexp(alpha, -eim);
     const int rb = row / brows, i = row - rb * brows;
-    for (int c = lane; c < K / 16; c += 32) {                            // 16 consecutive k -> one 16-byte chunk per slice
+    for (int c = gl; c < nchunk && live; c += G) {                       // 16 consecutive k -> one 16-byte chunk per slice
       const int k0 = c * 16, kb = k0 / KS, kk = k0 - kb * KS;
       unsigned char* base = img + (((m * nrb + rb) * nkb + kb) * slab);
       double yr[16], yi[16];
@@ -123,6 +131,16 @@ slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int6
       }
     }
   }
+}
+
+// 2^e as a double (|e| <= 1022), and an exact int32 -> double conversion without the conversion pipe:
+// the double with high word 0x43300000 and low word L is 2^52 + L
+__device__ __forceinline__ double exp2i(int e) {
+  e = e < -1022 ? -1022 : (e > 1023 ? 1023 : e);
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+__device__ __forceinline__ double i2d(int v) {
+  return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::i8 (int8 x int8 -> int32), issued by one thread
@@ -163,6 +181,7 @@ struct Params {
   int nkb, nrbX, ncbY, y_div, batch, conj_y;
   double* norm_out;            // [bz][tile] partial sums of |C|^2
   cx<double>* out_c;           // interleaved C[bz][M][N]
+  cx<double>* out_ct;          // interleaved transpose C^T[bz][N][M] (what the next application slices as r^T)
   const cx<double>* dot_with;  // dot_out[bz][tile] = sum conj(dot_with[bz][i][l]) C[i][l]
   cx<double>* dot_out;
 };
@@ -174,6 +193,7 @@ zgemm_i8_kernel(Params p) {
   __shared__ __align__(8) uint64_t s_bar[2 * NSTAGE + 2];
   __shared__ uint32_t s_tmem;
   __shared__ double s_red[4][4];
+  __shared__ double s_cs[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t dyn0 = smem_u32(smem_dyn);
   const uint32_t ring = (dyn0 + 1023u) & ~1023u;
@@ -256,8 +276,13 @@ zgemm_i8_kernel(Params p) {
       const int64_t bz = tile / tiles_per;
       const int rem = (int)(tile - bz * tiles_per), rbx = rem / p.ncbY, cby = rem - rbx * p.ncbY;
       const int row = rbx * XROWS + i;
-      const int exr = p.ex_x[(bz * M + row) * 2 + upper];
-      const int* eyp = p.ex_y + ((bz / p.y_div) * N + cby * YROWS) * 2;
+      const double rs = exp2i(p.ex_x[(bz * M + row) * 2 + upper]);
+      // column scales 2^ey of this tile, once per tile: s_cs[c] for Y re rows (c < 32) and im rows (c >= 32)
+      epi_bar();                               // everybody is done with the previous tile's s_cs / exchange buffer
+      if (prow < 64) {
+        const int* eyp = p.ex_y + ((bz / p.y_div) * N + cby * YROWS) * 2;
+        s_cs[prow] = exp2i(eyp[2 * (prow & 31) + (prow >> 5)]);
+      }
       mbar_wait(tfull_bar, accphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -271,24 +296,20 @@ zgemm_i8_kernel(Params p) {
         int v[32];
         tmem_ld32_i(taddr + (uint32_t)t * 64u, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fma((double)v[c], wgt, acc[c]);
+        for (int c = 0; c < 32; ++c) acc[c] = fma(i2d(v[c]), wgt, acc[c]);
         tmem_ld32_i(taddr + (uint32_t)t * 64u + 32u, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[32 + c] = fma((double)v[c], wgt, acc[32 + c]);
+        for (int c = 0; c < 32; ++c) acc[32 + c] = fma(i2d(v[c]), wgt, acc[32 + c]);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar);                 // this thread no longer reads the accumulators
       accphase ^= 1u;
-      // exponents: 2^(ex_row + ey_col)
+      epi_bar();                               // s_cs is complete
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        acc[c] = ldexp(acc[c], exr + eyp[2 * c]);
-        acc[32 + c] = ldexp(acc[32 + c], exr + eyp[2 * c + 1]);
-      }
+      for (int c = 0; c < 64; ++c) acc[c] *= rs * s_cs[c];
       // lower thread (Xr row): acc = [RR | RI];  upper thread (Xi row): acc = [IR | II].
       // lower keeps complex columns 0..15 and gives RR, RI of columns 16..31; upper the other way round.
       // (static register indices on both sides of every select: a run-time offset would push acc[] to local memory)
-      epi_bar();                               // the exchange buffer is free again
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         xch[g * 128 + prow] = upper ? make_double2(acc[2 * g], acc[2 * g + 1]) : make_double2(acc[16 + 2 * g], acc[16 + 2 * g + 1]);
@@ -321,6 +342,11 @@ zgemm_i8_kernel(Params p) {
         double2* o = reinterpret_cast<double2*>(p.out_c + ((bz * M + row) * (int64_t)N + col0));
 #pragma unroll
         for (int c = 0; c < 16; ++c) o[c] = make_double2(cre[c], cim[c]);
+      }
+      if (p.out_ct) {                          // lanes = consecutive rows: every store instruction writes 512 contiguous bytes
+        double2* o = reinterpret_cast<double2*>(p.out_ct + ((bz * N + col0) * (int64_t)M + row));
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[(int64_t)c * M] = make_double2(cre[c], cim[c]);
       }
       double dr = 0.0, di = 0.0;
       if (p.dot_with) {
