@@ -67,7 +67,12 @@ int zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void*
 }
 
 bool tm_power_i8_applies(int d, int D, int64_t N) {
-  return option_get(OPT_I8_POWER) && D >= 64 && D % 64 == 0 && d >= 1 && (int64_t)d * D < (1 << 19) && N * d < ((int64_t)1 << 30);
+  // option i8_power: 0 = never, 1 = where it is measured faster than the FP64 tensor pipe (D >= 128:
+  // profiles/exp_i8_r02*.jsonl; at D = 64 one slab per tile leaves the epilogue and the slicing pass exposed and DMMA
+  // wins), 2 = whenever the shapes allow
+  const int mode = option_get(OPT_I8_POWER);
+  if (!mode || (mode == 1 && D < 128)) return false;
+  return D >= 64 && D % 64 == 0 && d >= 1 && (int64_t)d * D < (1 << 19) && N * d < ((int64_t)1 << 30);
 }
 
 static __global__ void __launch_bounds__(256)

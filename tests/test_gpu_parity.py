@@ -1072,6 +1072,7 @@ def test_tm_power_complex128_tcgen05_vs_oracle_and_dmma(env, D, cnt, K):
     t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
     A, Bt = tensors(D, cnt, 4000 + D, O), tensors(D, cnt, 5000 + D, O)
     lib = L.load()
+    lib.qmps_set_option(b"i8_power", 2)          # force the int8 path (the default picks it from D = 128 up)
     r, ray = B.tm_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), K)
     lib.qmps_set_option(b"i8_power", 0)
     try:

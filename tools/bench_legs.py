@@ -303,10 +303,10 @@ def finish_energy_d8(torch, B, raw, ms_max, world, peaks):
     return res
 
 
-def leg_power(torch, B, dev, D, peaks, cdt_name, scale=1.0):
+def leg_power(torch, B, dev, D, peaks, cdt_name, scale=1.0, nprob=None):
     """cfg 5: K = 32 normalised applications r <- sum_s A_s r B_s^dagger on N problems (512 at D = 64, 32 at 256)."""
     cdt = torch.complex128 if cdt_name == "c128" else torch.complex64
-    N = max(2, int((512 if D == 64 else 32) * scale))
+    N = nprob or max(2, int((512 if D == 64 else 32) * scale))
     K = 32
     g = torch.Generator(device=dev).manual_seed(4)
 
@@ -320,20 +320,24 @@ def leg_power(torch, B, dev, D, peaks, cdt_name, scale=1.0):
     ms = timed_ms(torch, lambda: B.tm_power(A, Bt, K), reps=3, warm=1)
     apps = N * (K + 1)
     flops = 32.0 * D ** 3
-    if cdt_name == "c128":
+    achieved = apps * flops / ms * 1e3 / 1e12
+    i8 = cdt_name == "c128" and D >= 128 and D % 64 == 0           # qmps_tm_power's default dispatch (option i8_power = 1)
+    if i8:
+        peak, pipe, kern = peaks.get("i8_tcgen05_tops") or 2.0 * (peaks.get("bf16_tflops") or 1620.5), "tcgen05 kind::i8 (TOP/s)", "zgemm_i8_kernel"
+        issued, what = achieved * 21.0, "; 21 exact int8 slice products issued per algorithmic real product"
+    elif cdt_name == "c128":
         peak, pipe, kern = peaks["fp64_dmma_tflops"], "fp64 tensor (DMMA)", "zgemm_dmma_kernel"
+        issued, what = achieved, ""
     else:
         peak, pipe, kern = peaks.get("tf32_tcgen05_tflops") or (peaks.get("bf16_tflops") or 1620.5) / 2.0, \
             "tcgen05 kind::tf32" + ("" if peaks.get("tf32_tcgen05_tflops") else " (peak = half the measured bf16 figure; not measured directly)"), "cgemm_tc_kernel"
-    achieved = apps * flops / ms * 1e3 / 1e12
-    if cdt_name == "c64":
-        achieved_issued = achieved * 3.0       # 3xTF32: hi.hi + hi.lo + lo.hi per real product
+        issued, what = achieved * 3.0, "; 3 TF32 products issued per algorithmic product (hi.hi + hi.lo + lo.hi)"
     res = {"cfg": 5, "workload": f"power_method_D{D}_N{N}_K{K}_{cdt_name}", "metric": "transfer_matrix_applications_per_sec",
            "unit": "applications/s", "dtype": cdt_name, "value": apps / ms * 1e3, "ms_per_step": ms, "units_per_step": apps,
            "api": "qmps_tm_power",
-           "roofline": _roof("tensor", achieved if cdt_name == "c128" else achieved_issued, peak, "TFLOP/s", kern,
-                             f"{flops:.4g} real flops (32 D^3)" + ("; 3 TF32 products issued per algorithmic product" if cdt_name == "c64" else ""),
-                             note=pipe)}
+           "roofline": _roof("tensor", issued, peak, "TOP/s" if i8 else "TFLOP/s", kern, f"{flops:.4g} real flops (32 D^3)" + what, note=pipe)}
+    if i8:
+        res["roofline"]["vs_fp64_tensor_pipe"] = achieved / peaks["fp64_dmma_tflops"]
     res["roofline"]["algorithmic_tflops"] = achieved
     Ah, Bh = A.cpu().numpy(), Bt.cpu().numpy()
 
