@@ -26,6 +26,9 @@ int launch_env_real(qmps::EnvParams p, cudaStream_t st) {
   return 0;
 }
 
+// D = 8 complex128 with the elimination on the FP64 tensor pipe (kernels_envdmma.cuh, compiled in capi_envdmma.cu)
+int launch_env_dmma(int mode, qmps::EnvParams p, cudaStream_t st);
+
 // true if the fast path applies
 inline bool env_real_applies(const qmps::EnvParams& p) {
   return option_get(OPT_ENV_REAL) && p.assume_lc && (p.D == 4 || p.D == 8) && p.d >= 1 && p.d <= 4;
@@ -34,9 +37,14 @@ inline bool env_real_applies(const qmps::EnvParams& p) {
 template <typename REAL, int MODE>
 int dispatch_env_real(const qmps::EnvParams& p, cudaStream_t st) {
   if (p.D == 4) return launch_env_real<REAL, 4, MODE, 0>(p, st);
-  // er_wide: -1 = measured best per precision (profiles/sweep_er_r01*.jsonl), 0 / 1 / 2 force a variant
+  // er_wide: -1 = measured best per precision (profiles/sweep_er_r01*.jsonl, sweep_er_r02*.jsonl), 0 / 1 / 2 force a
+  // row-per-thread variant, 3 = blocked elimination on the FP64 tensor pipe (complex128 only)
   int v = option_get(OPT_ER_WIDE);
-  if (v < 0) v = sizeof(REAL) == 4 ? 2 : 0;
+  if (v < 0) v = sizeof(REAL) == 4 ? 2 : 3;
+  if (v == 3) {
+    if constexpr (sizeof(REAL) == 8) return launch_env_dmma(MODE, p, st);
+    v = 2;
+  }
   if (v == 1) return launch_env_real<REAL, 8, MODE, 1>(p, st);
   if (v == 2) return launch_env_real<REAL, 8, MODE, 2>(p, st);
   return launch_env_real<REAL, 8, MODE, 0>(p, st);

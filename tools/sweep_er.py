@@ -23,7 +23,7 @@ def main():
     flops = 8 * 2 * 8 ** 4 + (8.0 / 3.0) * 8 ** 6
     ref = None
     for cdt, tag in ((torch.complex128, "c128"), (torch.complex64, "c64")):
-        for wide in (0, 1, 2, 0, 1, 2):
+        for wide in ((0, 3, 0, 3) if tag == 'c128' else (0, 2)):
             lib.qmps_set_option(b"er_wide", wide)
             fn = lambda: B.energy_theta(prog, theta, H, coord=5, shifts=B.ROTO3_SHIFTS, dtype=cdt)
             e = fn()
