@@ -383,6 +383,7 @@ def run_ours(args):
                                      "kernel": "env_d2_stream_kernel<false,true>", "algorithmic_per_unit": f"{ALGO_BYTES_PER_SOLVE} B", "traffic": None}}
             leg("cfg2_steady", steady)
             torch.cuda.empty_cache()
+            leg("cfg1_scalar", lambda: BL.leg_scalar_latency(torch, dev))
             leg("cfg7", lambda: BL.leg_loschmidt(torch, B, R, dev, 2, peaks, scale=args.sub_scale))
             leg("cfg3", lambda: BL.leg_loschmidt(torch, B, R, dev, 4, peaks, scale=args.sub_scale))
             for D in (64, 256):

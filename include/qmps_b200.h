@@ -113,6 +113,10 @@ int qmps_env_exact(int d, int D, int64_t N, const void* in, int in_is_full_U,
 int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_U,
                         int assume_left_canonical, void* eta, void* r, void* C, int32_t* status,
                         int dtype, int device);
+/* the scalar drop-in in one call: get_env_exact(U) (qmps/tools.py:176-182) on HOST buffers,
+ *     U [N][2D][2D] -> V [N][D^2][D^2] = environment_to_unitary(cholesky(r)), status [N] (optional).
+ *     One H2D, three kernels, one D2H, one stream synchronisation. */
+int qmps_get_env_exact_host(int D, int64_t N, const void* U, void* V, int32_t* status, int dtype, int device);
 
 /* a6  Map(A,B).right_fixed_point() / .left_fixed_point() (xmps; call sites
  *     qmps/time_evolve_tools.py:87, qmps/loschmidts/time_evo.py:79-82):

@@ -448,4 +448,38 @@ int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_
   return rc;
 }
 
+// ---- the scalar drop-in in ONE call (qmps/tools.py:176-182 get_env_exact): U -> V on host buffers -----------------
+// H2D of the unitaries, environment solve (eta, r, Cholesky C), environment_to_unitary(C), D2H of V and the status
+// words, one stream synchronisation.  The Python mirror used to make six API calls with three host syncs per solve.
+int qmps_get_env_exact_host(int D, int64_t N, const void* U, void* V, int32_t* status, int dtype, int device) {
+  if (N < 0 || (N && (!U || !V))) return fail(QMPS_ERR_ARG, "get_env_exact_host: bad arguments");
+  if (!is_pow2(D) || D > 16) return fail(QMPS_ERR_UNSUPPORTED, "get_env_exact_host: unsupported D");
+  if (device < 0 || device >= 64) return fail(QMPS_ERR_ARG, "get_env_exact_host: bad device");
+  if (N == 0) return 0;
+  CK(cudaSetDevice(device));
+  const size_t csz = dtype == QMPS_C128 ? 16 : 8;
+  const int n = D * D;
+  const size_t u_per = csz * 4 * n, c_per = csz * n, v_per = csz * (size_t)n * n;
+  struct Slot { cudaStream_t st; char* buf; size_t cap; };
+  static std::mutex mu[64];
+  static Slot slots[64];
+  std::lock_guard<std::mutex> lock(mu[device]);
+  Slot& s = slots[device];
+  const size_t need = (size_t)N * (u_per + c_per + v_per + 16);
+  if (!s.st) CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  if (s.cap < need) {
+    if (s.buf) { cudaFree(s.buf); s.buf = nullptr; s.cap = 0; }
+    CK(cudaMalloc((void**)&s.buf, need));
+    s.cap = need;
+  }
+  char* dU = s.buf; char* dC = dU + (size_t)N * u_per; char* dV = dC + (size_t)N * c_per; char* dS = dV + (size_t)N * v_per;
+  CK(cudaMemcpyAsync(dU, U, (size_t)N * u_per, cudaMemcpyHostToDevice, s.st));
+  if (int rc = env_exact_any(2, D, N, dU, 1, 1, nullptr, nullptr, dC, (int32_t*)dS, dtype, s.st)) return rc;
+  if (int rc = qmps_environment_to_unitary(n, N, dC, dV, dtype, (void*)s.st)) return rc;
+  CK(cudaMemcpyAsync(V, dV, (size_t)N * v_per, cudaMemcpyDeviceToHost, s.st));
+  if (status) CK(cudaMemcpyAsync(status, dS, (size_t)N * 4, cudaMemcpyDeviceToHost, s.st));
+  CK(cudaStreamSynchronize(s.st));
+  return 0;
+}
+
 }  // extern "C"

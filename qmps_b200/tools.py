@@ -157,9 +157,26 @@ def env_exact_parts(U):
 
 
 def get_env_exact(U):
-    """Exact environment unitary V of a state unitary U (qmps/tools.py:176-182)."""
-    _, _, C = env_exact_parts(U)
-    return environment_to_unitary(C)
+    """Exact environment unitary V of a state unitary U (qmps/tools.py:176-182): one C-ABI call on host buffers
+    (``qmps_get_env_exact_host``: H2D, solve, Cholesky, environment_to_unitary, D2H, a single synchronisation)."""
+    from . import _lib
+    U = np.ascontiguousarray(np.asarray(U, dtype=np.complex128))
+    D = U.shape[0] // 2
+    V = np.empty((D * D, D * D), dtype=np.complex128)
+    st = np.zeros(1, dtype=np.int32)
+    lib = _lib.require_device()
+    _lib.check(lib.qmps_get_env_exact_host(D, 1, U.ctypes.data, V.ctypes.data, st.ctypes.data, _lib.C128, _device_index()),
+               "get_env_exact_host")
+    if st[0] == _lib.ST_NOT_PD:
+        raise LinAlgError("environment is not positive definite (Cholesky failed)")
+    if st[0] == _lib.ST_SINGULAR:
+        raise LinAlgError("transfer matrix has a degenerate leading eigenvalue")
+    return V
+
+
+def _device_index():
+    import torch
+    return torch.cuda.current_device()
 
 
 def get_env_exact_alternative(U):

@@ -348,3 +348,31 @@ def leg_power(torch, B, dev, D, peaks, cdt_name, scale=1.0, nprob=None):
     res["e2e"] = {"value": apps / ms_e * 1e3, "unit": "applications/s", "h2d_bytes_per_step": Ah.nbytes + Bh.nbytes,
                   "d2h_bytes_per_step": N * D * D * Ah.itemsize + N * Ah.itemsize, "api": "batched.tm_power on numpy inputs (pageable H2D, D2H of r_K and the Rayleigh quotients)"}
     return res
+
+
+def leg_scalar_latency(torch, dev):
+    """Batch-of-one drop-in latency: ``qmps_b200.tools.get_env_exact(U)`` (one C-ABI call on host buffers, one
+    synchronisation) against the oracle port of qmps/tools.py:176-182 on one host core, same 4 x 4 unitaries."""
+    import time
+    from scipy.stats import unitary_group
+    from qmps_b200 import tools as T
+    import oracle as O
+    Us = [unitary_group.rvs(4, random_state=300 + k) for k in range(64)]
+    for U in Us[:8]:
+        T.get_env_exact(U); O.get_env_exact(U)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        for U in Us:
+            T.get_env_exact(U)
+    gpu_us = (time.perf_counter() - t0) / (4 * len(Us)) * 1e6
+    t0 = time.perf_counter()
+    for U in Us:
+        O.get_env_exact(U)
+    cpu_us = (time.perf_counter() - t0) / len(Us) * 1e6
+    err = max(float(np.abs(np.abs(T.get_env_exact(U)[:, 0]) - np.abs(O.get_env_exact(U)[:, 0])).max()) for U in Us[:8])
+    return {"cfg": 1, "workload": "get_env_exact_batch_of_one_D2_c128 (scalar drop-in latency)", "metric": "latency_per_call", "unit": "us",
+            "dtype": "c128", "value": gpu_us, "higher_is_better": False, "api": "qmps_b200.tools.get_env_exact -> qmps_get_env_exact_host (H2D, 3 kernels, D2H, 1 sync)",
+            "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port", "sample": "64 per-call oracle.get_env_exact (qmps/tools.py:176-182 restated)"},
+            "max_abs_diff_first_column_moduli": err,
+            "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "kernel": "env_d2_stream_kernel + env2u_kernel",
+                         "note": "three launches + two PCIe copies + one synchronisation; nothing here is throughput-bound"}}
