@@ -145,8 +145,9 @@ int env_generic_f32(const qmps::EnvParams& p, int mode, cudaStream_t st);
 int fixed_point_f64(const qmps::FpParams& p, cudaStream_t st);
 int fixed_point_f32(const qmps::FpParams& p, cudaStream_t st);
 int fp16_debug_f64(unsigned long long* out, int reset);
-int ansatz_f64(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
-int ansatz_f32(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, cudaStream_t st);
+// coord / dshifts (DEVICE) / nshift: rotosolve shift fan-out, output index n * nshift + s (nshift = 0: plain)
+int ansatz_f64(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, int coord, const double* dshifts, int nshift, cudaStream_t st);
+int ansatz_f32(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, int coord, const double* dshifts, int nshift, cudaStream_t st);
 // capi_tc_i8.cu
 bool i8_shape_ok(int M, int N, int K);
 int zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C, cudaStream_t st);

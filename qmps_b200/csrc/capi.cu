@@ -262,8 +262,8 @@ int qmps_ansatz(const qmps_gate_op* ops, int nops, int nq, int64_t N, int P, con
   cudaStream_t st = (cudaStream_t)stream;
   GateOp* dops = nullptr;
   if (int rc = to_device_async((const GateOp*)ops, (size_t)nops, &dops, st)) return rc;
-  int rc = dtype == QMPS_C128 ? ansatz_f64(dops, nops, nq, N, P, theta, full_unitary, out, st)
-                              : ansatz_f32(dops, nops, nq, N, P, theta, full_unitary, out, st);
+  int rc = dtype == QMPS_C128 ? ansatz_f64(dops, nops, nq, N, P, theta, full_unitary, out, -1, nullptr, 0, st)
+                              : ansatz_f32(dops, nops, nq, N, P, theta, full_unitary, out, -1, nullptr, 0, st);
   if (dops) CK(cudaFreeAsync(dops, st));
   return rc;
 }
@@ -287,6 +287,26 @@ int qmps_energy_theta(const qmps_gate_op* ops, int nops, int nq, int64_t N, int 
   const int D = 1 << (nq - 1);
   if (D == 2 && nops <= d2_max_ops()) {
     rc = energy_d2_theta(dops, nops, N, P, theta, hmat, coord, dsh, nshift, energy, status, dtype, st);
+  } else if (D == 8 && dtype == QMPS_C128 && option_get(OPT_ENV_REAL) && (option_get(OPT_ER_WIDE) < 0 || option_get(OPT_ER_WIDE) == 3)) {
+    // phase split (measured: profiles/exp_split_r02*.json): the ansatz runs as its own high-occupancy kernel and leaves
+    // the tensors in HBM (2 KB per evaluation), the 200-register solve kernel starts from them.  Chunked so that the
+    // scratch stays below 512 MiB.
+    const int S = nshift > 0 ? nshift : 1;
+    const int64_t chunk = ((int64_t)1 << 18) / S;
+    Scratch scratch(st);
+    cx<double>* At = nullptr;
+    const int64_t first = N < chunk ? N : chunk;
+    if (scratch.get(&At, sizeof(cx<double>) * (size_t)first * S * 128) != cudaSuccess) rc = fail(QMPS_ERR_CUDA, "energy_theta: scratch allocation failed");
+    for (int64_t off = 0; off < N && !rc; off += chunk) {
+      const int64_t cnt = (N - off < chunk) ? (N - off) : chunk;
+      rc = ansatz_f64(dops, nops, nq, cnt, P, theta + off * P, 0, At, coord, dsh, nshift, st);
+      if (rc) break;
+      EnvParams p;
+      memset(&p, 0, sizeof(p));
+      p.d = 2; p.D = D; p.N = cnt * S; p.in = At; p.assume_lc = 1; p.status = status ? status + off * S : nullptr; p.coord = -1;
+      p.hmat = hmat; p.energy = (double*)energy + off * S; p.two_site = 0;
+      rc = env_generic_f64(p, 1, st);
+    }
   } else {
     EnvParams p;
     memset(&p, 0, sizeof(p));

@@ -158,7 +158,7 @@ template <int G> int launch_fp(FpParams p, cudaStream_t st) {
 
 template <int G>
 int launch_ansatz(const GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out,
-                  cudaStream_t st) {
+                  int coord, const double* dshifts, int nshift, cudaStream_t st) {
   const int R = 1 << nq, nc = full ? R : R / 2;
   const size_t per = (((size_t)R * nc * sizeof(cx<REAL>) + 15) & ~size_t(15)) + (((size_t)2 * nops * sizeof(REAL) + 15) & ~size_t(15));
   const int block = G > 32 ? G : 128;
@@ -167,8 +167,8 @@ int launch_ansatz(const GateOp* dops, int nops, int nq, int64_t N, int P, const 
   auto kern = ansatz_kernel<REAL, G>;
   if (int rc = allow_smem(kern, smem)) return rc;
   int grid = 1;
-  if (int rc = persistent_grid(kern, block, smem, (N + gpc - 1) / gpc, &grid)) return rc;
-  kern<<<grid, block, smem, st>>>(dops, nops, nq, N, P, theta, full, (cx<REAL>*)out);
+  if (int rc = persistent_grid(kern, block, smem, (N * (nshift > 0 ? nshift : 1) + gpc - 1) / gpc, &grid)) return rc;
+  kern<<<grid, block, smem, st>>>(dops, nops, nq, N, P, theta, full, (cx<REAL>*)out, coord, dshifts, nshift);
   CK(cudaGetLastError());
   return 0;
 }
@@ -191,10 +191,10 @@ int fixed_point_f32(const FpParams& p, cudaStream_t st) {
   }
 }
 int ansatz_f32(const GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out,
-               cudaStream_t st) {
+               int coord, const double* dshifts, int nshift, cudaStream_t st) {
   const int R = 1 << nq, elems = R * (full ? R : R / 2);
-  return elems <= 8 ? launch_ansatz<4>(dops, nops, nq, N, P, theta, full, out, st)
-       : elems <= 64 ? launch_ansatz<16>(dops, nops, nq, N, P, theta, full, out, st)
-                     : launch_ansatz<32>(dops, nops, nq, N, P, theta, full, out, st);
+  return elems <= 8 ? launch_ansatz<4>(dops, nops, nq, N, P, theta, full, out, coord, dshifts, nshift, st)
+       : elems <= 64 ? launch_ansatz<16>(dops, nops, nq, N, P, theta, full, out, coord, dshifts, nshift, st)
+                     : launch_ansatz<32>(dops, nops, nq, N, P, theta, full, out, coord, dshifts, nshift, st);
 }
 }  // namespace qmps_host

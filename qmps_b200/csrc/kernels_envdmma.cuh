@@ -90,7 +90,7 @@ __device__ __forceinline__ cx<double> ed_G(const cx<double>* Ai, const cx<double
 // tile column and the four pivot steps of a panel are run-time loops, which keeps the kernel inside the instruction
 // cache (the fully unrolled first version spent a quarter of its stall samples on instruction fetch).
 template <int MODE, int DP>
-__global__ void __launch_bounds__(64, 6)
+__global__ void __maxnreg__(168)
 env_dmma_kernel(EnvParams p) {
   typedef double T;
   constexpr int D = 8, n = 64;
@@ -107,7 +107,6 @@ env_dmma_kernel(EnvParams p) {
   T* Lb = reinterpret_cast<T*>(base + L.Lb);
   T* Ub = reinterpret_cast<T*>(base + L.Ub);
   T* recbuf = reinterpret_cast<T*>(base + L.rec);
-  T* candbuf = reinterpret_cast<T*>(base + L.cand);
   T* xs = reinterpret_cast<T*>(base + L.x);
   T* xraw = reinterpret_cast<T*>(base + L.xraw);
   cx<T>* r = reinterpret_cast<cx<T>*>(base + L.r);
@@ -120,6 +119,9 @@ env_dmma_kernel(EnvParams p) {
   const cx<T>* hmat = reinterpret_cast<const cx<T>*>(p.hmat);
   const int e = threadIdx.x;                                 // panel role: my row of the array
   const int w = e >> 5, lane = e & 31, q = lane >> 2, t = lane & 3;   // fragment role
+  // which warp factorises the panels: alternates with the CTA's residency slot (p.ws_stride = SM count), so that the
+  // heavier panel warps spread over all four SM sub-partitions instead of piling up on two of them
+  const int pw = p.ws_stride ? (int)((blockIdx.x / (unsigned)p.ws_stride) & 1u) : 0;
   if (e < 32) {
     int j = 0, l = 0;
     if (e < 28) ed_pair(e, &j, &l);
@@ -201,99 +203,119 @@ env_dmma_kernel(EnvParams p) {
       }
     }
 
-    // ---- 3. blocked Gauss-Jordan
-    bool done = false;
+    // ---- 3. blocked Gauss-Jordan.  The panel is factorised by warp 0 alone, two rows per lane (rows lane and
+    //         lane + 32), pivot rows broadcast by shuffles: no CTA barrier inside the four pivot steps.
+    bool doneA = false, doneB = false;
     int bad = 0;
-    int mycol = 0;
+    int colA = 0, colB = 0;
+    int* Rb = reinterpret_cast<int*>(recbuf);                // the four pivot rows of the current block
 #pragma unroll
     for (int cbK = 0; cbK < 8; ++cbK) {
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int K = 2 * cbK + h;
         const int NJ = (K == 15) ? 3 : 4;
-        // panel columns 4K .. 4K+3 from the fragments to one-thread-per-row form
+        // panel columns 4K .. 4K+3 from the fragments to row-major form
         if ((t >> 1) == h) {
 #pragma unroll
           for (int rbl = 0; rbl < 4; ++rbl)
             *reinterpret_cast<double2*>(Pb + (8 * (4 * w + rbl) + q) * 4 + 2 * (t & 1)) = make_double2(acc[rbl][cbK][0], acc[rbl][cbK][1]);
         }
         g.sync();
-        double pv4[4], wv[4] = {0.0, 0.0, 0.0, 0.0};
-        {
-          const double2 v0 = *reinterpret_cast<const double2*>(Pb + e * 4), v1 = *reinterpret_cast<const double2*>(Pb + e * 4 + 2);
-          pv4[0] = v0.x; pv4[1] = v0.y; pv4[2] = v1.x; pv4[3] = v1.y;
-        }
-        int mine = -1;                                        // the pivot step of this block that took my row
-#pragma unroll 1
-        for (int j = 0; j < NJ; ++j) {
-          const T pj = j == 0 ? pv4[0] : (j == 1 ? pv4[1] : (j == 2 ? pv4[2] : pv4[3]));
-          unsigned key = done ? 0u : ((__float_as_uint((float)fabs(pj)) & ~63u) | (unsigned)(63 - e));
-          if (!done && key < 64u) key = 64u | (unsigned)(63 - e);
-          const unsigned best = __reduce_max_sync(0xffffffffu, key);
-          const int who = 63 - (int)(best & 63u);
-          T* rec = recbuf + ((j & 1) * 2 + w) * 8;
-          T* cb2 = candbuf + ((j & 1) * 2 + w) * 2;
-          if (e == who && best != 0u) {
-            *reinterpret_cast<double2*>(rec) = make_double2(pv4[0], pv4[1]);
-            *reinterpret_cast<double2*>(rec + 2) = make_double2(pv4[2], pv4[3]);
-            *reinterpret_cast<double2*>(rec + 4) = make_double2(wv[0], wv[1]);
-            *reinterpret_cast<double2*>(rec + 6) = make_double2(wv[2], wv[3]);
-            *reinterpret_cast<double2*>(cb2) = make_double2((T)__uint_as_float(best & ~63u), T(who));
-          }
-          if (best == 0u && lane == 0) cb2[0] = T(-1);          // this warp has no unused row left
-          g.sync();
-          const double2 c0 = *reinterpret_cast<const double2*>(candbuf + ((j & 1) * 2) * 2);
-          const double2 c1 = *reinterpret_cast<const double2*>(candbuf + ((j & 1) * 2 + 1) * 2);
-          const int bw = (c1.x > c0.x) ? 1 : 0;
-          const T cand = bw ? c1.x : c0.x;
-          const int gwho = (int)(bw ? c1.y : c0.y);
-          const T* prec = recbuf + ((j & 1) * 2 + bw) * 8;
-          if (!(cand > tiny_of<T>::v())) bad = 1;
-          double row[8];                                      // pivot row: panel part [0..3], W part [4..7] with W[j] = 1
+        if (w == pw) {
+          double pA[4], pB[4], wA[4] = {0.0, 0.0, 0.0, 0.0}, wB[4] = {0.0, 0.0, 0.0, 0.0};
           {
-            const double2 r0 = *reinterpret_cast<const double2*>(prec), r1 = *reinterpret_cast<const double2*>(prec + 2);
-            const double2 r2 = *reinterpret_cast<const double2*>(prec + 4), r3 = *reinterpret_cast<const double2*>(prec + 6);
-            row[0] = r0.x; row[1] = r0.y; row[2] = r1.x; row[3] = r1.y;
-            row[4] = r2.x; row[5] = r2.y; row[6] = r3.x; row[7] = r3.y;
+            const double2 a0 = *reinterpret_cast<const double2*>(Pb + lane * 4), a1 = *reinterpret_cast<const double2*>(Pb + lane * 4 + 2);
+            const double2 b0 = *reinterpret_cast<const double2*>(Pb + (lane + 32) * 4), b1 = *reinterpret_cast<const double2*>(Pb + (lane + 32) * 4 + 2);
+            pA[0] = a0.x; pA[1] = a0.y; pA[2] = a1.x; pA[3] = a1.y;
+            pB[0] = b0.x; pB[1] = b0.y; pB[2] = b1.x; pB[3] = b1.y;
           }
-          const T pvt = j == 0 ? row[0] : (j == 1 ? row[1] : (j == 2 ? row[2] : row[3]));
-          const T inv = T(1) / pvt;
+          int mineA = -1, mineB = -1;
+          int rsel[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { row[c] *= inv; row[4 + c] = (c == j) ? inv : row[4 + c] * inv; }
-          // every row but the pivot row: x -= x[j] * (scaled pivot row); the pivot row becomes the scaled row.
-          // (panel entries left of j and W entries right of j are dead / zero, so all eight are treated alike)
-          if (e == gwho) {
+          for (int j = 0; j < 4; ++j) {
+            if (j < NJ) {
+              // arg-max of |column j| over the unused rows: 32-bit key = top bits of the magnitude as a float | (63 - row)
+              unsigned kA = doneA ? 0u : ((__float_as_uint((float)fabs(pA[j])) & ~63u) | (unsigned)(63 - lane));
+              unsigned kB = doneB ? 0u : ((__float_as_uint((float)fabs(pB[j])) & ~63u) | (unsigned)(31 - lane));
+              if (!doneA && kA < 64u) kA = 64u | (unsigned)(63 - lane);
+              if (!doneB && kB < 64u) kB = 64u | (unsigned)(31 - lane);
+              const unsigned best = __reduce_max_sync(0xffffffffu, kA > kB ? kA : kB);
+              const int who = 63 - (int)(best & 63u);
+              const int wl = who & 31;
+              const bool isB = who >= 32;
+              if (!(__uint_as_float(best & ~63u) > 1e-13f)) bad = 1;
+              rsel[j] = who;
+              // pivot row: panel entries j.., W entries ..j-1, from its lane
+              double row[4], wrow[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { pv4[c] = row[c]; wv[c] = row[4 + c]; }
-            done = true; mine = j; mycol = 4 * K + j;
-          } else {
+              for (int c = 0; c < 4; ++c) {
+                if (c >= j) row[c] = __shfl_sync(0xffffffffu, isB ? pB[c] : pA[c], wl);
+                if (c < j) wrow[c] = __shfl_sync(0xffffffffu, isB ? wB[c] : wA[c], wl);
+              }
+              const double inv = 1.0 / row[j];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { pv4[c] = fma(-pj, row[c], pv4[c]); wv[c] = fma(-pj, row[4 + c], wv[c]); }
+              for (int c = 0; c < 4; ++c) {
+                if (c > j) row[c] *= inv;
+                if (c < j) wrow[c] *= inv;
+              }
+              // every other row: x -= x[j] * (scaled pivot row); the pivot row becomes the scaled row
+              {
+                const bool piv = (who == lane);
+                const double f = pA[j];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (c > j) pA[c] = piv ? row[c] : fma(-f, row[c], pA[c]);
+                  if (c < j) wA[c] = piv ? wrow[c] : fma(-f, wrow[c], wA[c]);
+                }
+                wA[j] = piv ? inv : -f * inv;
+                if (piv) { doneA = true; mineA = j; colA = 4 * K + j; }
+              }
+              {
+                const bool piv = (who == lane + 32);
+                const double f = pB[j];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (c > j) pB[c] = piv ? row[c] : fma(-f, row[c], pB[c]);
+                  if (c < j) wB[c] = piv ? wrow[c] : fma(-f, wrow[c], wB[c]);
+                }
+                wB[j] = piv ? inv : -f * inv;
+                if (piv) { doneB = true; mineB = j; colB = 4 * K + j; }
+              }
+            }
           }
-          // the raw pivot row out of its owner's fragments: Ub[col][j]
-          const int prb = gwho >> 3, pq = gwho & 7;
-          if ((prb >> 2) == w && q == pq) {
-            T* ub = Ub + 8 * t + j;
-            switch (prb & 3) {
+          // -L = W - E_R
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { wA[c] -= (mineA == c) ? 1.0 : 0.0; wB[c] -= (mineB == c) ? 1.0 : 0.0; }
+          if (K == 15) { wA[3] = 0.0; wB[3] = 0.0; }
+          *reinterpret_cast<double2*>(Lb + lane * 4) = make_double2(wA[0], wA[1]);
+          *reinterpret_cast<double2*>(Lb + lane * 4 + 2) = make_double2(wA[2], wA[3]);
+          *reinterpret_cast<double2*>(Lb + (lane + 32) * 4) = make_double2(wB[0], wB[1]);
+          *reinterpret_cast<double2*>(Lb + (lane + 32) * 4 + 2) = make_double2(wB[2], wB[3]);
+          if (lane == 0) *reinterpret_cast<int4*>(Rb) = make_int4(rsel[0], rsel[1], rsel[2], rsel[3]);
+        }
+        g.sync();
+        // the raw pivot rows out of their owners' fragments: Ub[col][j]
+        {
+          const int4 R4 = *reinterpret_cast<const int4*>(Rb);
+#pragma unroll 1
+          for (int j = 0; j < NJ; ++j) {
+            const int gwho = j == 0 ? R4.x : (j == 1 ? R4.y : (j == 2 ? R4.z : R4.w));
+            const int prb = gwho >> 3, pq = gwho & 7;
+            if ((prb >> 2) == w && q == pq) {
+              T* ub = Ub + 8 * t + j;
+              switch (prb & 3) {
 #define QMPS_ED_PUB(rr)                                                              \
   case rr:                                                                           \
     _Pragma("unroll") for (int cb = 0; cb < 8; ++cb) {                               \
       if (cb >= cbK) { ub[32 * cb] = acc[rr][cb][0]; ub[32 * cb + 4] = acc[rr][cb][1]; } \
     }                                                                                \
     break;
-              QMPS_ED_PUB(0) QMPS_ED_PUB(1) QMPS_ED_PUB(2) QMPS_ED_PUB(3)
+                QMPS_ED_PUB(0) QMPS_ED_PUB(1) QMPS_ED_PUB(2) QMPS_ED_PUB(3)
 #undef QMPS_ED_PUB
+              }
             }
           }
-        }
-        // -L = W - E_R
-        {
-          double l4[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) l4[c] = wv[c] - ((mine == c) ? 1.0 : 0.0);
-          if (K == 15) l4[3] = 0.0;
-          *reinterpret_cast<double2*>(Lb + e * 4) = make_double2(l4[0], l4[1]);
-          *reinterpret_cast<double2*>(Lb + e * 4 + 2) = make_double2(l4[2], l4[3]);
           if (K == 15) Ub[e * 4 + 3] = 0.0;
         }
         g.sync();
@@ -319,7 +341,10 @@ env_dmma_kernel(EnvParams p) {
       for (int rbl = 0; rbl < 4; ++rbl) xraw[8 * (4 * w + rbl) + q] = acc[rbl][7][1];
     }
     g.sync();
-    if (done) xs[mycol] = xraw[e];
+    if (w == pw) {
+      if (doneA) xs[colA] = xraw[lane];
+      if (doneB) xs[colB] = xraw[lane + 32];
+    }
     g.sync();
     {
       const int a = e >> 3, b = e & 7;

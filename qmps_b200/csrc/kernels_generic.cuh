@@ -251,7 +251,8 @@ fixed_point_kernel(FpParams p) {
 template <typename T, int G>
 __global__ void __launch_bounds__(G > 32 ? G : 128)
 ansatz_kernel(const GateOp* __restrict__ ops, int nops, int nq, int64_t N, int P,
-              const double* __restrict__ theta, int full_unitary, cx<T>* __restrict__ out) {
+              const double* __restrict__ theta, int full_unitary, cx<T>* __restrict__ out,
+              int coord, const double* __restrict__ shifts, int nshift) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   int gi, gpc;
   const Grp g = make_group<G>(&gi, &gpc);
@@ -262,8 +263,12 @@ ansatz_kernel(const GateOp* __restrict__ ops, int nops, int nq, int64_t N, int P
   cx<T>* S = reinterpret_cast<cx<T>*>(base);
   T* trig = reinterpret_cast<T*>(base + (((size_t)R * nc * sizeof(cx<T>) + 15) & ~size_t(15)));
   StateLayout SL; SL.R = R; SL.ncols = nc; SL.a_layout = full_unitary ? 0 : 1;
-  for (int64_t pid = (int64_t)blockIdx.x * gpc + gi; pid < N; pid += (int64_t)gridDim.x * gpc) {
-    ansatz_eval<T>(g, ops, nops, theta + pid * P, -1, 0.0, nq, SL, S, trig);
+  // shift fan-out (rotosolve): output (n, s) is the tensor of theta[n] + shifts[s] e_coord, index n * nshift + s
+  const int SF = nshift > 0 ? nshift : 1;
+  for (int64_t pid = (int64_t)blockIdx.x * gpc + gi; pid < N * SF; pid += (int64_t)gridDim.x * gpc) {
+    const int64_t pn = pid / SF;
+    const double sh = nshift > 0 ? shifts[(int)(pid - pn * SF)] : 0.0;
+    ansatz_eval<T>(g, ops, nops, theta + pn * P, nshift > 0 ? coord : -1, sh, nq, SL, S, trig);
     cx<T>* o = out + pid * (size_t)(R * nc);
     for (int e = g.lane; e < R * nc; e += g.size) o[e] = S[e];
     g.sync();
