@@ -310,6 +310,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     assert torch.equal(hr.to(dev), r[0]) and torch.equal(heta.to(dev), eta[0]) and torch.equal(hC.to(dev), C[0]), \
         "host-buffer path disagrees with device path"
+    # the same call with PACKED outputs (64-byte records: Hermitian trace-1 r as 3 reals, triangular C as 4, status;
+    # eta = 1 on the canonical path) -- same information, 64 instead of 148 bytes back over the link
+    hpk = torch.empty((N, 8), dtype=torch.float64).pin_memory()
+
+    def e2e_packed_step():
+        L.check(lib.qmps_env_exact_packed_host(N, hin.data_ptr(), 0, hpk.data_ptr(), local_rank), "env_exact_packed_host")
+
+    e2e_packed_step(); e2e_packed_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_packed_step()
+    barrier()
+    tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e_packed_value = world * N * e2e_steps / float(tp.item())
+    pk = hpk.to(dev)
+    ok0 = status[0] == 0
+    assert torch.equal(pk[:, 7].to(torch.int32), status[0]) and torch.equal(pk[:, 0], r[0][:, 0, 0].real) \
+        and torch.equal(pk[:, 1], r[0][:, 0, 1].real) and torch.equal(pk[:, 2], r[0][:, 0, 1].imag) \
+        and torch.equal(pk[:, 3][ok0], C[0][:, 0, 0].real[ok0]) and torch.equal(pk[:, 6][ok0], C[0][:, 1, 1].real[ok0]) \
+        and torch.equal(pk[:, 4][ok0], C[0][:, 1, 0].real[ok0]) and torch.equal(pk[:, 5][ok0], C[0][:, 1, 0].imag[ok0]), \
+        "packed host path disagrees with device path"
+    del pk, hpk
     # what the link alone allows: the same bytes as plain pinned copies, both directions at once, no kernel
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     din = torch.empty_like(A[0])
@@ -412,8 +437,12 @@ def run_ours(args):
                          "algorithmic_bytes_per_solve": ALGO_BYTES_PER_SOLVE,
                          "kernel_ms": k_ms, "traffic": dram_traffic_from_profile(),
                          "traffic_note": "ncu --set full, one launch of this kernel with rotated outputs: dram__bytes_read.sum + dram__bytes_write.sum (profiles/roofline_traffic.json)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * N, "d2h_bytes_per_step": 148 * N,
-                    "steps": e2e_steps, "api": "qmps_env_exact_host (C ABI, pinned host buffers, chunked 3-stream pipeline), all four outputs",
+            "e2e": {"value": e2e_packed_value, "unit": UNIT, "h2d_bytes_per_step": 128 * N, "d2h_bytes_per_step": 64 * N,
+                    "steps": e2e_steps,
+                    "api": "qmps_env_exact_packed_host (C ABI, pinned host buffers, chunked 3-stream pipeline): eta, r, C, status as one 64-byte "
+                           "record per solve (Hermitian trace-1 r = 3 reals, lower-triangular C = 4 reals, status; eta = 1 on the canonical path)",
+                    "full_outputs_value": e2e_value,
+                    "full_outputs_note": "qmps_env_exact_host writing eta[N], r[N,2,2], C[N,2,2], status[N] unpacked: 148 B/solve back; link_bound_per_gpu refers to these bytes",
                     "link_bound_per_gpu": link_value,
                     "link_bound_note": "same H2D+D2H bytes as plain concurrent pinned copies, no kernel (solves/s, rank 0)"},
             "gpu_launches": args.steps * world,

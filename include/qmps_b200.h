@@ -113,6 +113,14 @@ int qmps_env_exact(int d, int D, int64_t N, const void* in, int in_is_full_U,
 int qmps_env_exact_host(int d, int D, int64_t N, const void* in, int in_is_full_U,
                         int assume_left_canonical, void* eta, void* r, void* C, int32_t* status,
                         int dtype, int device);
+/* a4/a5, D = 2 complex128 left-canonical, PACKED outputs: one 64-byte record per solve
+ *     [ r00, Re r01, Im r01, c00, Re c10, Im c10, c11, (double) status ]
+ *     (r Hermitian trace 1: r11 = 1 - r00, r10 = conj r01; C lower triangular with real positive diagonal: c01 = 0;
+ *     eta = 1 on this path) -- the same information as eta / r / C / status of qmps_env_exact in 64 instead of 148
+ *     bytes; the host-buffer path is bound by the PCIe link, so this is what a bandwidth-conscious caller binds.
+ *     in: A [N][2][2][2] (in_is_full_U = 0) or U [N][4][4]; packed [N][8] doubles (DEVICE / HOST). */
+int qmps_env_exact_packed(int64_t N, const void* in, int in_is_full_U, void* packed, void* stream);
+int qmps_env_exact_packed_host(int64_t N, const void* in, int in_is_full_U, void* packed, int device);
 /* the scalar drop-in in one call: get_env_exact(U) (qmps/tools.py:176-182) on HOST buffers,
  *     U [N][2D][2D] -> V [N][D^2][D^2] = environment_to_unitary(cholesky(r)), status [N] (optional).
  *     One H2D, three kernels, one D2H, one stream synchronisation. */

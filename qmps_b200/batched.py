@@ -119,6 +119,42 @@ def env_exact(A=None, U=None, assume_left_canonical=True, want_eta=True, want_r=
     return EnvResult(eta, r, C, st)
 
 
+def env_exact_packed(A=None, U=None):
+    """D = 2 complex128 left-canonical environments as 64-byte records (``qmps_env_exact_packed``):
+    ``packed[N, 8] = [r00, Re r01, Im r01, c00, Re c10, Im c10, c11, status]``; ``unpack_env`` expands them."""
+    if (A is None) == (U is None):
+        raise ValueError("pass exactly one of A, U")
+    x = _cdev(A if A is not None else U, torch.complex128)
+    N = x.shape[0]
+    out = torch.empty((N, 8), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().qmps_env_exact_packed(N, _p(x), int(U is not None), _p(out), _stream()), "env_exact_packed")
+    return out
+
+
+def env_exact_packed_host(x, is_unitary=False, out=None, device=0):
+    """Host-buffer form (numpy in, numpy out; pinned buffers make it link-bound): x = A[N,2,2,2] or U[N,4,4]."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    N = x.shape[0]
+    if out is None:
+        out = np.empty((N, 8), dtype=np.float64)
+    L.check(L.require_device().qmps_env_exact_packed_host(N, x.ctypes.data, int(bool(is_unitary)), out.ctypes.data, int(device)),
+            "env_exact_packed_host")
+    return out
+
+
+def unpack_env(packed):
+    """packed[N, 8] (numpy) -> (eta[N] = 1, r[N,2,2], C[N,2,2], status[N]): the outputs of ``env_exact``."""
+    p = np.asarray(packed)
+    N = p.shape[0]
+    r = np.empty((N, 2, 2), dtype=np.complex128)
+    C = np.zeros((N, 2, 2), dtype=np.complex128)
+    r[:, 0, 0] = p[:, 0]; r[:, 1, 1] = 1.0 - p[:, 0]
+    r[:, 0, 1] = p[:, 1] + 1j * p[:, 2]; r[:, 1, 0] = p[:, 1] - 1j * p[:, 2]
+    C[:, 0, 0] = p[:, 3]; C[:, 1, 0] = p[:, 4] + 1j * p[:, 5]; C[:, 1, 1] = p[:, 6]
+    return np.ones(N, dtype=np.complex128), r, C, p[:, 7].astype(np.int32)
+
+
 # ---- a6 / a8 / a11 ---------------------------------------------------------------------
 def fixed_point(A, B, pair="elementwise", left=False, want_vec=True, want_costs=True, want_status=True,
                 gauge="zgeev"):

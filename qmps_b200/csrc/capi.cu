@@ -502,4 +502,48 @@ int qmps_get_env_exact_host(int D, int64_t N, const void* U, void* V, int32_t* s
   return 0;
 }
 
+// ---- packed D = 2 outputs: 64 B per solve instead of 148 B (the host link is what bounds the host-buffer path) ------
+int qmps_env_exact_packed(int64_t N, const void* in, int in_is_full_U, void* packed, void* stream) {
+  if (N < 0 || (N && (!in || !packed))) return fail(QMPS_ERR_ARG, "env_exact_packed: bad arguments");
+  return env_d2_packed(N, in, in_is_full_U, packed, (cudaStream_t)stream);
+}
+int qmps_env_exact_packed_host(int64_t N, const void* in, int in_is_full_U, void* packed, int device) {
+  if (N < 0 || (N && (!in || !packed))) return fail(QMPS_ERR_ARG, "env_exact_packed_host: bad arguments");
+  if (device < 0 || device >= 64) return fail(QMPS_ERR_ARG, "env_exact_packed_host: bad device");
+  if (N == 0) return 0;
+  CK(cudaSetDevice(device));
+  const size_t in_per = in_is_full_U ? 256 : 128, out_per = 64;
+  int64_t chunk = (int64_t)((16u << 20) / in_per);
+  if (chunk > N) chunk = N;
+  const int NS = 3;
+  struct Slot { cudaStream_t st; char* din; char* dout; };
+  static std::mutex mu[64];
+  static Slot slots[64][NS];
+  static size_t cap[64] = {0};
+  std::lock_guard<std::mutex> lock(mu[device]);
+  Slot* sl = slots[device];
+  if (cap[device] < (size_t)chunk) {
+    cap[device] = 0;
+    for (int k = 0; k < NS; ++k) {
+      if (sl[k].din) { cudaFree(sl[k].din); sl[k].din = nullptr; }
+      if (sl[k].dout) { cudaFree(sl[k].dout); sl[k].dout = nullptr; }
+      if (!sl[k].st) CK(cudaStreamCreateWithFlags(&sl[k].st, cudaStreamNonBlocking));
+      CK(cudaMalloc((void**)&sl[k].din, (size_t)chunk * 256));
+      CK(cudaMalloc((void**)&sl[k].dout, (size_t)chunk * out_per));
+    }
+    cap[device] = (size_t)chunk;
+  }
+  int rc = 0, k = 0;
+  for (int64_t off = 0; off < N && !rc; off += chunk, k = (k + 1) % NS) {
+    const int64_t cnt = (N - off < chunk) ? (N - off) : chunk;
+    Slot& s = sl[k];
+    CK(cudaMemcpyAsync(s.din, (const char*)in + (size_t)off * in_per, (size_t)cnt * in_per, cudaMemcpyHostToDevice, s.st));
+    rc = env_d2_packed(cnt, s.din, in_is_full_U, s.dout, s.st);
+    if (rc) break;
+    CK(cudaMemcpyAsync((char*)packed + (size_t)off * out_per, s.dout, (size_t)cnt * out_per, cudaMemcpyDeviceToHost, s.st));
+  }
+  for (int q = 0; q < NS; ++q) if (sl[q].st) CK(cudaStreamSynchronize(sl[q].st));
+  return rc;
+}
+
 }  // extern "C"

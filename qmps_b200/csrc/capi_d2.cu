@@ -6,14 +6,15 @@
 using namespace qmps;
 namespace qmps_host {
 namespace {
+int32_t* const kPackedTag = reinterpret_cast<int32_t*>(~uintptr_t(0));   // internal marker: write packed records
 int env_exact_d2_c128(int64_t N, const void* in, int in_is_U, void* eta, void* r, void* C, int32_t* status,
                       cudaStream_t st) {
   const int64_t ntiles = (N + 31) / 32;
   const int64_t blocks = (ntiles + D2_WARPS - 1) / D2_WARPS;
   int grid = 1;
-#define QMPS_D2_LAUNCH(INU, WC)                                                                           \
+#define QMPS_D2_LAUNCH(INU, WC, ...)                                                                      \
   do {                                                                                                    \
-    auto kern = env_d2_stream_kernel<INU, WC>;                                                            \
+    auto kern = env_d2_stream_kernel<INU, WC, ##__VA_ARGS__>;                                             \
     if (int rc = allow_smem(kern, D2_SMEM_BYTES)) return rc;                                              \
     if (int rc = persistent_grid(kern, D2_WARPS * 32, D2_SMEM_BYTES, blocks, &grid)) return rc;          \
     if (option_get(OPT_D2_CTAS_PER_SM) > 0) {                                                             \
@@ -31,7 +32,10 @@ int env_exact_d2_c128(int64_t N, const void* in, int in_is_U, void* eta, void* r
     CK(cudaLaunchKernelEx(&cfg, kern, (const cx<double>*)in, N, (cx<double>*)eta, (cx<double>*)r,         \
                           (cx<double>*)C, status));                                                       \
   } while (0)
-  if (in_is_U) { if (C) QMPS_D2_LAUNCH(true, true); else QMPS_D2_LAUNCH(true, false); }
+  if (status == kPackedTag) {                  // packed 64-byte records through r (env_d2_packed)
+    status = nullptr;
+    if (in_is_U) QMPS_D2_LAUNCH(true, true, true); else QMPS_D2_LAUNCH(false, true, true);
+  } else if (in_is_U) { if (C) QMPS_D2_LAUNCH(true, true); else QMPS_D2_LAUNCH(true, false); }
   else { if (C) QMPS_D2_LAUNCH(false, true); else QMPS_D2_LAUNCH(false, false); }
 #undef QMPS_D2_LAUNCH
   CK(cudaGetLastError());
@@ -57,6 +61,12 @@ int env_d2(int64_t N, const void* in, int in_is_U, void* eta, void* r, void* C, 
   if (N == 0) return 0;
   if (dtype == QMPS_C128) return env_exact_d2_c128(N, in, in_is_U, eta, r, C, status, st);
   return env_exact_d2_simple<float>(N, in, in_is_U, eta, r, C, status, st);
+}
+
+// D = 2 complex128, left-canonical: one 64-byte record per problem (layout: kernels_d2.cuh)
+int env_d2_packed(int64_t N, const void* in, int in_is_U, void* packed, cudaStream_t st) {
+  if (N == 0) return 0;
+  return env_exact_d2_c128(N, in, in_is_U, nullptr, packed, nullptr, kPackedTag, st);
 }
 
 int energy_d2_theta(const GateOp* dops, int nops, int64_t N, int P, const double* theta, const void* hmat, int coord,

@@ -60,7 +60,9 @@ __device__ __forceinline__ void d2_issue_tile(const cx<double>* __restrict__ in,
   }
 }
 
-template <bool IN_U, bool WANT_C>
+// PACKED: one 64-byte record per problem through r_out instead of eta / r / C / status (see qmps_env_exact_packed):
+//   [ r00, Re r01, Im r01, c00, Re c10, Im c10, c11, (double) status ]   (r11 = 1 - r00, r10 = conj r01, c01 = 0, eta = 1)
+template <bool IN_U, bool WANT_C, bool PACKED = false>
 __global__ void __launch_bounds__(D2_WARPS * 32, 2)
 env_d2_stream_kernel(const cx<double>* __restrict__ in, int64_t N, cx<double>* __restrict__ eta_out,
                      cx<double>* __restrict__ r_out, cx<double>* __restrict__ C_out,
@@ -97,7 +99,12 @@ env_d2_stream_kernel(const cx<double>* __restrict__ in, int64_t N, cx<double>* _
     double eta;
     const int st = env_d2_solve<double, WANT_C>(a, r, &eta, C);
     const int64_t gp = tile * 32 + lane;
-    if (gp < N) {
+    if (PACKED) {
+      const cx<double> P0 = mk<double>(r[0].re, r[1].re), P1 = mk<double>(r[1].im, C[0].re);
+      const cx<double> P3 = mk<double>(C[3].re, (double)st);
+      r[0] = P0; r[1] = P1; r[2] = C[2]; r[3] = P3;
+    }
+    if (!PACKED && gp < N) {
       if (eta_out) st_stream16(eta_out + gp, mk<double>(eta, 0.0));
       if (status_out) status_out[gp] = st;
     }
@@ -113,7 +120,7 @@ env_d2_stream_kernel(const cx<double>* __restrict__ in, int64_t N, cx<double>* _
       }
       __syncwarp();
     }
-    if (WANT_C) {
+    if (WANT_C && !PACKED) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) ost[lane * 4 + (e ^ ((lane >> 1) & 3))] = C[e];
       __syncwarp();

@@ -76,6 +76,31 @@ def test_env_d2_full_size_properties(env):
     assert C[:, 0, 1].abs().max() == 0 and (C[:, 0, 0].imag.abs().max() == 0)
 
 
+@pytest.mark.parametrize("N,use_U", [(1, False), (1000, True), (4099, False)])
+def test_env_d2_packed_records_equal_full_outputs(env, N, use_U):
+    """qmps_env_exact_packed(+_host): the 64-byte records expand to the eta / r / C / status of qmps_env_exact."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    from scipy.stats import unitary_group
+    U = np.stack([unitary_group.rvs(4, random_state=7000 + k) for k in range(min(N, 64))])
+    U = np.tile(U, (N // len(U) + 1, 1, 1))[:N].copy()
+    A = np.stack([O.unitary_to_tensor(u) for u in U[:64]]); A = np.tile(A, (N // len(A) + 1, 1, 1, 1))[:N].copy()
+    if N > 1:                                                # a product state: status NOT_PD travels in the record
+        U[N // 2] = np.eye(4)
+        A[N // 2] = O.unitary_to_tensor(np.eye(4))
+    x = U if use_U else A
+    full = B.env_exact(**({"U": t.from_numpy(x).cuda()} if use_U else {"A": t.from_numpy(x).cuda()}))
+    packed = B.env_exact_packed(**({"U": t.from_numpy(x).cuda()} if use_U else {"A": t.from_numpy(x).cuda()})).cpu().numpy()
+    host = B.env_exact_packed_host(x, is_unitary=use_U)
+    assert np.array_equal(packed, host)
+    eta, r, C, st = B.unpack_env(packed)
+    st0 = full.status.cpu().numpy()
+    assert np.array_equal(st, st0) and (N == 1 or st[N // 2] == env["L"].ST_NOT_PD)
+    ok = st0 == 0
+    assert np.abs(r[ok] - full.r.cpu().numpy()[ok]).max() < 1e-12
+    assert np.abs(C[ok] - full.C.cpu().numpy()[ok]).max() < 1e-12
+    assert np.abs(eta[ok] - full.eta.cpu().numpy()[ok]).max() < 1e-12
+
+
 def test_env_d2_not_positive_definite_is_flagged(env):
     """Product state: r has rank one, the reference's cholesky raises LinAlgError (tools.py:182)."""
     t, B, L = env["torch"], env["B"], env["L"]
