@@ -350,6 +350,17 @@ int qmps_loschmidt_trajectory(const qmps_gate_op* ops, int nops, int nq, int P, 
                               int n_steps, int n_gen, int npop, double sigma0, uint64_t seed, int n_bfgs, double* theta_traj,
                               void* step_cost, void* echo, int dtype, void* stream);
 
+/* (f)-4 PXP scar dynamics (the reference's scars.py, a caller of Map(merge(A1,A2), merge(A1',A2')).right_fixed_point()):
+ *     cost [N] = -2 |<0|C|0>| of scars_time_evolve_cost_function / scars_cost_fun_alternate (scars.py:76-155) for
+ *     candidate angles params [N][4] = [theta1, phi1, phi2, theta2] against current [NC][4] (NC = 1: shared, or N);
+ *     W: DEVICE [16][16] complex, the four-site gate expm(+i dt H(mu)) (scars.py:23-29); eta [N] (optional): the
+ *     leading eigenvalue of the mixed two-site map.  trajectory: simulate_scars (scars.py:157-170) on the device --
+ *     traj [n_steps+1][4] DEVICE (row 0 = params0), step_cost [n_steps] optional. */
+int qmps_scars_cost(int64_t N, const double* params, int64_t NC, const double* current, const void* W, void* cost,
+                    void* eta, int32_t* status, int dtype, void* stream);
+int qmps_scars_trajectory(const double* params0, const void* W, int n_steps, int n_gen, int npop, double sigma0,
+                          uint64_t seed, int n_bfgs, double* traj, void* step_cost, int dtype, void* stream);
+
 /* (e)  the final cost reduction across ranks: local argmin, one ncclAllGather of 16 bytes per
  *     rank and a final pass, all on `stream`; best_cost [1] / best_index [1] are DEVICE scalars, identical on
  *     every rank (ties: smallest global index; an empty shard contributes nothing).  `comm` is an ncclComm_t --

@@ -57,3 +57,4 @@ from .canonical import *    # noqa: F401,F403
 from .brickwall import *    # noqa: F401,F403
 from .stacked import *      # noqa: F401,F403
 from .tdvp import *         # noqa: F401,F403
+from .scars import *        # noqa: F401,F403

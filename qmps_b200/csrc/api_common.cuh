@@ -146,6 +146,7 @@ int fixed_point_f64(const qmps::FpParams& p, cudaStream_t st);
 int fixed_point_f32(const qmps::FpParams& p, cudaStream_t st);
 int fp16_debug_f64(unsigned long long* out, int reset);
 // coord / dshifts (DEVICE) / nshift: rotosolve shift fan-out, output index n * nshift + s (nshift = 0: plain)
+int scars_cost_any(int64_t N, const double* params, int64_t NC, const double* current, const void* W, void* cost, void* eta, int32_t* status, int dtype, cudaStream_t st);
 int env_d2_packed(int64_t N, const void* in, int in_is_U, void* packed, cudaStream_t st);
 int ansatz_f64(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, int coord, const double* dshifts, int nshift, cudaStream_t st);
 int ansatz_f32(const qmps::GateOp* dops, int nops, int nq, int64_t N, int P, const double* theta, int full, void* out, int coord, const double* dshifts, int nshift, cudaStream_t st);

@@ -416,6 +416,76 @@ int qmps_loschmidt_trajectory(const qmps_gate_op* ops, int nops, int nq, int P, 
   return 0;
 }
 
+
+// ---- (f)-4 PXP scar dynamics (the reference's scars.py): batched step cost and the whole trajectory on the device -----
+int qmps_scars_cost(int64_t N, const double* params, int64_t NC, const double* current, const void* W, void* cost, void* eta,
+                    int32_t* status, int dtype, void* stream) {
+  if (N < 0 || (N && (!params || !current || !W || !cost)) || (NC != 1 && NC != N))
+    return fail(QMPS_ERR_ARG, "scars_cost: bad arguments (NC must be 1 or N)");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "scars_cost: bad dtype");
+  return scars_cost_any(N, params, NC, current, W, cost, eta, status, dtype, (cudaStream_t)stream);
+}
+
+// simulate_scars (scars.py:157-170): per time step minimise the step cost over the four angles, starting from the
+// current ones -- here a Gaussian population (one launch per generation) followed by BFGS with batched
+// finite-difference gradients, the argmin fed back on the device.  traj [n_steps + 1][4] (DEVICE, row 0 = params0),
+// step_cost [n_steps] (real of the precision, optional).
+int qmps_scars_trajectory(const double* params0, const void* W, int n_steps, int n_gen, int npop, double sigma0, uint64_t seed,
+                          int n_bfgs, double* traj, void* step_cost, int dtype, void* stream) {
+  const int P = 4;
+  if (!params0 || !W || n_steps < 0 || n_gen < 0 || n_bfgs < 0 || (n_gen && (npop < 8 || !(sigma0 > 0))) || !traj)
+    return fail(QMPS_ERR_ARG, "scars_trajectory: bad arguments");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "scars_trajectory: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = rsize(dtype);
+  Scratch scratch(st);
+  const int ncand = npop > 2 * P + 1 ? (npop > BFGS_LS ? npop : BFGS_LS) : (2 * P + 1 > BFGS_LS ? 2 * P + 1 : BFGS_LS);
+  double *cand = nullptr, *sigma = nullptr, *bc = nullptr, *cost64 = nullptr; long long* bi = nullptr; char* cost = nullptr;
+  double *bg = nullptr, *bgp = nullptr, *bs = nullptr, *bd = nullptr, *bH = nullptr, *bf0 = nullptr; int* bhave = nullptr;
+  CK(scratch.get(&bg, sizeof(double) * P)); CK(scratch.get(&bgp, sizeof(double) * P)); CK(scratch.get(&bs, sizeof(double) * P));
+  CK(scratch.get(&bd, sizeof(double) * P)); CK(scratch.get(&bH, sizeof(double) * P * P)); CK(scratch.get(&bf0, sizeof(double)));
+  CK(scratch.get(&bhave, sizeof(int)));
+  CK(scratch.get(&cand, sizeof(double) * (size_t)ncand * P));
+  CK(scratch.get(&sigma, sizeof(double))); CK(scratch.get(&bc, sizeof(double))); CK(scratch.get(&bi, sizeof(long long)));
+  CK(scratch.get(&cost, rs * ncand));
+  if (dtype != QMPS_C128) CK(scratch.get(&cost64, sizeof(double) * ncand));
+  CK(cudaMemcpyAsync(traj, params0, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+  const double* c64 = dtype == QMPS_C128 ? (const double*)cost : cost64;
+  for (int step = 0; step < n_steps; ++step) {
+    const double* cur = traj + (size_t)step * P;
+    double* centre = traj + (size_t)(step + 1) * P;
+    CK(cudaMemcpyAsync(centre, cur, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+    auto evaluate = [&](int n) -> int {
+      if (int rc = scars_cost_any(n, cand, 1, cur, W, cost, nullptr, nullptr, dtype, st)) return rc;
+      if (dtype != QMPS_C128) widen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const float*)cost, cost64);
+      return 0;
+    };
+    set_scalar_kernel<<<1, 32, 0, st>>>(sigma, sigma0);
+    for (int gen = 0; gen < n_gen; ++gen) {
+      es_propose_kernel<<<(npop * P + 255) / 256, 256, 0, st>>>(npop, P, centre, sigma, (unsigned long long)seed,
+                                                                (unsigned long long)step * (unsigned long long)n_gen + gen, cand);
+      if (int rc = evaluate(npop)) return rc;
+      if (int rc = qmps_argmin(npop, c64, 0, bc, (int64_t*)bi, stream)) return rc;
+      es_select_kernel<<<1, 64, 0, st>>>(P, cand, bi, bc, centre, sigma, nullptr);
+    }
+    const double hfd = dtype == QMPS_C128 ? 1e-5 : 3e-3;
+    if (n_bfgs > 0) bfgs_init_kernel<<<1, 64, 0, st>>>(P, bH, bhave);
+    for (int it = 0; it < n_bfgs; ++it) {
+      bfgs_probe_kernel<<<1, 256, 0, st>>>(P, centre, hfd, cand);
+      if (int rc = evaluate(2 * P + 1)) return rc;
+      bfgs_direction_kernel<<<1, 64, 0, st>>>(P, c64, hfd, bg, bgp, bs, bd, bH, bf0, bhave, centre, cand);
+      if (int rc = evaluate(BFGS_LS)) return rc;
+      bfgs_step_kernel<<<1, 64, 0, st>>>(P, c64, bd, bs, bf0, bhave, centre, bc);
+    }
+    if (step_cost) {
+      if (dtype == QMPS_C128) CK(cudaMemcpyAsync((double*)step_cost + step, bc, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      else narrow_kernel<<<1, 32, 0, st>>>(bc, (float*)step_cost + step);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- (e) cross-rank argmin over NCCL ------------------------------------------------------------------
 int qmps_nccl_unique_id(void* id128) {
   Nccl* n;
