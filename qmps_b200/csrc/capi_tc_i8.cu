@@ -17,13 +17,17 @@ int launch_slice(int64_t nmat, int R, int K, const Z* in, int64_t mstride, int64
                  cudaStream_t st) {
   if (nmat * R == 0) return 0;
   int G = 1;
-  while (G < 32 && G * 2 <= K / 16) G *= 2;                 // lanes per row
+  while (G < 32 && G < K / 16) G *= 2;                      // lanes per row: the power of two >= K / 16 chunks (<= 32)
   const int64_t warps = (nmat * R + (32 / G) - 1) / (32 / G);
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  tci8::slice_kernel<<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kin, kstride, kostride, is_y, norm_in,
-                                                       n_in, a_div, img, ex, G);
+  if (K / 16 <= G)
+    tci8::slice_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kin, kstride, kostride, is_y, norm_in,
+                                                               n_in, a_div, img, ex, G);
+  else
+    tci8::slice_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kin, kstride, kostride, is_y, norm_in,
+                                                                n_in, a_div, img, ex, G);
   CK(cudaGetLastError());
   return 0;
 }

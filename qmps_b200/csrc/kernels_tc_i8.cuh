@@ -58,7 +58,8 @@ QMPS_HD uint32_t img_off(int prow, int bcol) {
 // stage 2 then accumulates exactly in the integer accumulators).  is_y: blocks of 32 rows instead of 64.
 // scale (optional): value multiplied by rsqrt(sum_j norm_in[(m / a_div) * n_in + j]) before slicing.
 // One warp per (matrix, complex row).  ex[(m * R + row) * 2 + part]: exponent e, x ~ 2^e sum q_p 2^{-7(p+1)}.
-static __global__ void __launch_bounds__(256)
+template <bool SINGLE>
+static __global__ void __launch_bounds__(256, 2)
 slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int64_t mstride, int64_t rstride, int kin,
              int64_t kstride, int64_t kostride, int is_y, const double* __restrict__ norm_in, int n_in, int a_div,
              unsigned char* __restrict__ img, int* __restrict__ ex, int G) {
@@ -85,12 +86,27 @@ slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int6
     }
     const cx<double>* src = in + m * mstride + row * rstride;
     double mre = 0.0, mim = 0.0;
-    for (int c = gl; c < nchunk; c += G) {
-#pragma unroll 4
+    // one chunk per lane (K <= 512): the 16 elements are loaded ONCE, all 16 loads in flight, and stay in registers
+    // for the slicing below (the kernel is bound by global-load latency: profiles/ncu_slice_r02e.txt)
+    constexpr bool single = SINGLE;                  // nchunk <= G, decided by the launcher
+    cx<double> zc[16];
+    if (single) {
+      const int c = gl < nchunk ? gl : nchunk - 1;
+#pragma unroll
       for (int t = 0; t < 16; ++t) {
         const int k = c * 16 + t;
-        const cx<double> z = src[(k / kin) * kostride + (k % kin) * kstride];
-        mre = fmax(mre, fabs(z.re)); mim = fmax(mim, fabs(z.im));
+        zc[t] = src[(k / kin) * kostride + (k % kin) * kstride];
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) { mre = fmax(mre, fabs(zc[t].re)); mim = fmax(mim, fabs(zc[t].im)); }
+    } else {
+      for (int c = gl; c < nchunk; c += G) {
+#pragma unroll 4
+        for (int t = 0; t < 16; ++t) {
+          const int k = c * 16 + t;
+          const cx<double> z = src[(k / kin) * kostride + (k % kin) * kstride];
+          mre = fmax(mre, fabs(z.re)); mim = fmax(mim, fabs(z.im));
+        }
       }
     }
     for (int o = G >> 1; o > 0; o >>= 1) {
@@ -101,28 +117,49 @@ slice_kernel(int64_t nmat, int R, int K, const cx<double>* __restrict__ in, int6
     if (mre * alpha > 0.0) { frexp(mre * alpha, &ere); ere += 1; }      // |x| / 2^e < 1/2
     if (mim * alpha > 0.0) { frexp(mim * alpha, &eim); eim += 1; }
     if (live && gl == 0) { ex[(m * R + row) * 2] = ere; ex[(m * R + row) * 2 + 1] = eim; }
-    const double sre = ldexp(alpha, -ere), sim = ldexp(alpha, -eim);
+    // Fixed point, not floating point: v = round(x 2^(42 - e)) as a 64-bit integer by the magic-number add (one DFMA;
+    // |v| <= 2^41).  Adding the bias B = 64 (1 + 128 + ... + 128^5) makes every balanced base-128 digit d_p = u_p - 64
+    // non-negative, so the six slices are plain bit fields of v + B -- no carry chain: a funnel shift and a mask per
+    // digit, four digits per 32-bit word, and one SWAR byte-wise subtraction of 64 per word.  (The first version cut the
+    // slices with rint / double->int conversions and the second with a serial carry chain; at ~110 integer
+    // instructions per real number the slicing passes cost as much as the GEMMs: profiles/launches_i8_r02*.csv.)
+    const double MAGIC = 6755399441055744.0;                             // 1.5 * 2^52: ulp = 1
+    constexpr long long BIAS = 64ll * ((1ll << 42) - 1) / 127;           // sum_p 64 * 128^p
+    const long long KSUB = 0x4338000000000000ll - BIAS;                  // bits(MAGIC) - B
+    const double sre = ldexp(alpha, 42 - ere), sim = ldexp(alpha, 42 - eim);
     const int rb = row / brows, i = row - rb * brows;
     for (int c = gl; c < nchunk && live; c += G) {                       // 16 consecutive k -> one 16-byte chunk per slice
       const int k0 = c * 16, kb = k0 / KS, kk = k0 - kb * KS;
       unsigned char* base = img + (((m * nrb + rb) * nkb + kb) * slab);
-      double yr[16], yi[16];
+      unsigned long long ur[16], ui[16];
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
         const int k = k0 + t;
-        const cx<double> z = src[(k / kin) * kostride + (k % kin) * kstride];
-        yr[t] = z.re * sre; yi[t] = z.im * sim;
+        const cx<double> z = single ? zc[t] : src[(k / kin) * kostride + (k % kin) * kstride];
+        ur[t] = (unsigned long long)(__double_as_longlong(fma(z.re, sre, MAGIC)) - KSUB);     // v + B >= 0
+        ui[t] = (unsigned long long)(__double_as_longlong(fma(z.im, sim, MAGIC)) - KSUB);
       }
 #pragma unroll
       for (int p = 0; p < NSL; ++p) {
+        const int sh = 7 * (NSL - 1 - p);                                // slice p has weight 128^(5 - p) in v
         uint32_t wr[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+        if (p > 0) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          yr[t] *= 128.0; yi[t] *= 128.0;
-          const double qr = rint(yr[t]), qi = rint(yi[t]);
-          yr[t] -= qr; yi[t] -= qi;
-          wr[t >> 2] |= ((uint32_t)(int)qr & 0xffu) << (8 * (t & 3));
-          wi[t >> 2] |= ((uint32_t)(int)qi & 0xffu) << (8 * (t & 3));
+          for (int t = 0; t < 16; ++t) {
+            wr[t >> 2] |= ((uint32_t)(ur[t] >> sh) & 127u) << (8 * (t & 3));
+            wi[t >> 2] |= ((uint32_t)(ui[t] >> sh) & 127u) << (8 * (t & 3));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                                  // bytes u in [0, 127] -> (u - 64) as int8
+            wr[q] = ((wr[q] | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
+            wi[q] = ((wi[q] | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
+          }
+        } else {                                                         // top digit: u <= 128, no mask
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            wr[t >> 2] |= ((uint32_t)((int)(ur[t] >> sh) - 64) & 0xffu) << (8 * (t & 3));
+            wi[t >> 2] |= ((uint32_t)((int)(ui[t] >> sh) - 64) & 0xffu) << (8 * (t & 3));
+          }
         }
         const int bcol = (p & 1) * 64 + kk;
         unsigned char* pl = base + (p >> 1) * plane;
