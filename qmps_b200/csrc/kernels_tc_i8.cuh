@@ -21,8 +21,10 @@
 // the TMA engine (cp.async.bulk + mbarrier complete_tx); no tensor map.
 //
 // Kernel: persistent, warp-specialised, 192 threads, 1 CTA per SM: warp 0 = TMA producer (2-stage ring, 72 KB per
-// stage), warp 1 = single-thread MMA issuer (42 UMMAs per slab), warps 2-5 = epilogue (tcgen05.ld of the six
-// accumulators, FP64 recombination, lane-pair exchange through shared memory, norms / dot products, stores).
+// stage), warp 1 = single-thread MMA issuer (42 UMMAs per slab), warps 2-9 = epilogue (tcgen05.ld of the six
+// accumulators, FP64 recombination, lane-pair exchange through shared memory, norms / dot products, stores): two warps
+// per TMEM lane quarter, each taking half of the tile's columns -- the FP64 recombination is the critical path of a tile
+// (profiles/ncu_i8gemm_r02f.txt), so it gets eight warps instead of four.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,7 +43,7 @@ constexpr int X_SLAB = 3 * X_PLANE, Y_SLAB = 3 * Y_PLANE;
 constexpr int STAGE_BYTES = X_SLAB + Y_SLAB;    // 73 728
 constexpr int NSTAGE = 2;
 constexpr int XCH_BYTES = 128 * 32 * 8;         // 32 doubles per epilogue thread
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                     // producer warp, MMA warp, eight epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + XCH_BYTES + 1024;
 
@@ -206,6 +208,20 @@ __device__ __forceinline__ void tmem_ld32_i(uint32_t taddr, int (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = (int)r[i];
 }
 
+__device__ __forceinline__ void tmem_ld16_i(uint32_t taddr, int (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (int)r[i];
+}
+__device__ __forceinline__ void epi_bar8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major,
 // N = 64 ((64 >> 3) << 17), M = 128 ((128 >> 4) << 24)
 constexpr uint32_t IDESC_I8_128x64 = (2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -229,7 +245,7 @@ zgemm_i8_kernel(Params p) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * NSTAGE + 2];
   __shared__ uint32_t s_tmem;
-  __shared__ double s_red[4][4];
+  __shared__ double s_red[8][4];
   __shared__ double s_cs[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t dyn0 = smem_u32(smem_dyn);
@@ -242,7 +258,7 @@ zgemm_i8_kernel(Params p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 128);
+    mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem), TMEM_COLS);
@@ -305,7 +321,9 @@ zgemm_i8_kernel(Params p) {
     __syncwarp();
   } else {
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int ew = warp - 2, h = ew >> 2;      // h: which half of the tile's 32 complex columns
     const int prow = 32 * q + lane;            // plane row of X = TMEM lane
+    const int tid_e = h * 128 + prow;
     const int i = prow & 63, upper = prow >> 6;
     const int M = p.nrbX * XROWS, N = p.ncbY * YROWS;
     uint32_t accphase = 0;
@@ -315,58 +333,58 @@ zgemm_i8_kernel(Params p) {
       const int row = rbx * XROWS + i;
       const double rs = exp2i(p.ex_x[(bz * M + row) * 2 + upper]);
       // column scales 2^ey of this tile, once per tile: s_cs[c] for Y re rows (c < 32) and im rows (c >= 32)
-      epi_bar();                               // everybody is done with the previous tile's s_cs / exchange buffer
-      if (prow < 64) {
+      epi_bar8();                              // everybody is done with the previous tile's s_cs / exchange buffer
+      if (tid_e < 64) {
         const int* eyp = p.ex_y + ((bz / p.y_div) * N + cby * YROWS) * 2;
-        s_cs[prow] = exp2i(eyp[2 * (prow & 31) + (prow >> 5)]);
+        s_cs[tid_e] = exp2i(eyp[2 * (tid_e & 31) + (tid_e >> 5)]);
       }
       mbar_wait(tfull_bar, accphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
-      // acc[c]: c < 32: (my X plane row) . (Y re row c);  c >= 32: . (Y im row c - 32); levels summed smallest first
-      double acc[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * h);
+      // acc[c], c < 16: (my X plane row) . (Y re row 16 h + c);  acc[16 + c]: . (Y im row 16 h + c); smallest level first
+      double acc[32];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+      for (int c = 0; c < 32; ++c) acc[c] = 0.0;
 #pragma unroll
       for (int t = NSL - 1; t >= 0; --t) {
         const double wgt = 1.0 / (double)(1ull << (7 * (t + 2)));
-        int v[32];
-        tmem_ld32_i(taddr + (uint32_t)t * 64u, v);
+        int v[16];
+        tmem_ld16_i(taddr + (uint32_t)t * 64u, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fma(i2d(v[c]), wgt, acc[c]);
-        tmem_ld32_i(taddr + (uint32_t)t * 64u + 32u, v);
+        for (int c = 0; c < 16; ++c) acc[c] = fma(i2d(v[c]), wgt, acc[c]);
+        tmem_ld16_i(taddr + (uint32_t)t * 64u + 32u, v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[32 + c] = fma(i2d(v[c]), wgt, acc[32 + c]);
+        for (int c = 0; c < 16; ++c) acc[16 + c] = fma(i2d(v[c]), wgt, acc[16 + c]);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar);                 // this thread no longer reads the accumulators
       accphase ^= 1u;
-      epi_bar();                               // s_cs is complete
+      epi_bar8();                              // s_cs is complete
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc[c] *= rs * s_cs[c];
-      // lower thread (Xr row): acc = [RR | RI];  upper thread (Xi row): acc = [IR | II].
-      // lower keeps complex columns 0..15 and gives RR, RI of columns 16..31; upper the other way round.
+      for (int c = 0; c < 16; ++c) { acc[c] *= rs * s_cs[16 * h + c]; acc[16 + c] *= rs * s_cs[32 + 16 * h + c]; }
+      // lower thread (Xr row): acc = [RR | RI];  upper thread (Xi row): acc = [IR | II]  (16 complex columns each).
+      // lower keeps local columns 0..7 and gives RR, RI of columns 8..15; upper the other way round.
       // (static register indices on both sides of every select: a run-time offset would push acc[] to local memory)
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        xch[g * 128 + prow] = upper ? make_double2(acc[2 * g], acc[2 * g + 1]) : make_double2(acc[16 + 2 * g], acc[16 + 2 * g + 1]);
-        xch[(8 + g) * 128 + prow] = upper ? make_double2(acc[32 + 2 * g], acc[32 + 2 * g + 1])
-                                          : make_double2(acc[48 + 2 * g], acc[48 + 2 * g + 1]);
+      for (int g = 0; g < 4; ++g) {
+        xch[g * 256 + tid_e] = upper ? make_double2(acc[2 * g], acc[2 * g + 1]) : make_double2(acc[8 + 2 * g], acc[8 + 2 * g + 1]);
+        xch[(4 + g) * 256 + tid_e] = upper ? make_double2(acc[16 + 2 * g], acc[16 + 2 * g + 1])
+                                           : make_double2(acc[24 + 2 * g], acc[24 + 2 * g + 1]);
       }
-      epi_bar();
-      const int partner = prow ^ 64, keep0 = upper ? 16 : 0;
+      epi_bar8();
+      const int partner = tid_e ^ 64, keep0 = 16 * h + (upper ? 8 : 0);
       const double sgn = p.conj_y ? 1.0 : -1.0;
-      double cre[16], cim[16], ssq = 0.0;
+      double cre[8], cim[8], ssq = 0.0;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const double2 p1 = xch[g * 128 + partner], p2 = xch[(8 + g) * 128 + partner];
+      for (int g = 0; g < 4; ++g) {
+        const double2 p1 = xch[g * 256 + partner], p2 = xch[(4 + g) * 256 + partner];
         const double P1[2] = {p1.x, p1.y}, P2[2] = {p2.x, p2.y};
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int c = 2 * g + e;
           double rr, ri, ir, ii;
-          if (!upper) { rr = acc[c]; ri = acc[32 + c]; ir = P1[e]; ii = P2[e]; }
-          else { ir = acc[16 + c]; ii = acc[48 + c]; rr = P1[e]; ri = P2[e]; }
+          if (!upper) { rr = acc[c]; ri = acc[16 + c]; ir = P1[e]; ii = P2[e]; }
+          else { ir = acc[8 + c]; ii = acc[24 + c]; rr = P1[e]; ri = P2[e]; }
           // no conj: Cr = RR - II, Ci = RI + IR;   conj(Y): Cr = RR + II, Ci = IR - RI
           cre[c] = rr + sgn * ii;
           cim[c] = ir - sgn * ri;
@@ -378,18 +396,18 @@ zgemm_i8_kernel(Params p) {
       if (p.out_c) {
         double2* o = reinterpret_cast<double2*>(p.out_c + ((bz * M + row) * (int64_t)N + col0));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = make_double2(cre[c], cim[c]);
+        for (int c = 0; c < 8; ++c) o[c] = make_double2(cre[c], cim[c]);
       }
       if (p.out_ct) {                          // lanes = consecutive rows: every store instruction writes 512 contiguous bytes
         double2* o = reinterpret_cast<double2*>(p.out_ct + ((bz * N + col0) * (int64_t)M + row));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[(int64_t)c * M] = make_double2(cre[c], cim[c]);
+        for (int c = 0; c < 8; ++c) o[(int64_t)c * M] = make_double2(cre[c], cim[c]);
       }
       double dr = 0.0, di = 0.0;
       if (p.dot_with) {
         const double2* w = reinterpret_cast<const double2*>(p.dot_with + ((bz * M + row) * (int64_t)N + col0));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
           const double2 z = w[c];
           dr += z.x * cre[c] + z.y * cim[c];
           di += z.x * cim[c] - z.y * cre[c];
@@ -402,14 +420,14 @@ zgemm_i8_kernel(Params p) {
           dr += __shfl_xor_sync(0xffffffffu, dr, o);
           di += __shfl_xor_sync(0xffffffffu, di, o);
         }
-        if (lane == 0) { s_red[q][0] = ssq; s_red[q][1] = dr; s_red[q][2] = di; }
-        epi_bar();
-        if (prow == 0) {
-          const double s = (s_red[0][0] + s_red[1][0]) + (s_red[2][0] + s_red[3][0]);
-          if (p.norm_out) p.norm_out[bz * tiles_per + tile_in] = s;
-          if (p.dot_out)
-            p.dot_out[bz * tiles_per + tile_in] = mk<double>((s_red[0][1] + s_red[1][1]) + (s_red[2][1] + s_red[3][1]),
-                                                             (s_red[0][2] + s_red[1][2]) + (s_red[2][2] + s_red[3][2]));
+        if (lane == 0) { s_red[ew][0] = ssq; s_red[ew][1] = dr; s_red[ew][2] = di; }
+        epi_bar8();
+        if (tid_e == 0) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { s0 += s_red[k][0]; s1 += s_red[k][1]; s2 += s_red[k][2]; }
+          if (p.norm_out) p.norm_out[bz * tiles_per + tile_in] = s0;
+          if (p.dot_out) p.dot_out[bz * tiles_per + tile_in] = mk<double>(s1, s2);
         }
       }
     }
