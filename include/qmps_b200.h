@@ -216,8 +216,7 @@ int qmps_cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* 
  *     X [batch][M][K], Y [batch][N][K], C [batch][M][N] complex128, M % 64 == 0, N % 32 == 0, K % 64 == 0.
  *     Every real operand row is cut into six signed 7-bit slices under a power-of-two row scale; the 21 slice
  *     products with i + j < 6 are exact int32 tensor-core products, recombined in FP64 (relative error ~4e-12).
- *     qmps_tm_power uses it for complex128 when D % 64 == 0 and D >= 128 (option "i8_power": 0 never, 1 measured
- *     crossover, 2 always). */
+ *     qmps_tm_power uses it for complex128 when D % 64 == 0 (option "i8_power": 0 = FP64 tensor pipe instead). */
 int qmps_zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void* Y, int conj_y, void* C,
                        void* stream);
 

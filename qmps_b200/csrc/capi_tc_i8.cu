@@ -71,11 +71,10 @@ int zgemm_c128_i8(int64_t batch, int M, int N, int K, const void* X, const void*
 }
 
 bool tm_power_i8_applies(int d, int D, int64_t N) {
-  // option i8_power: 0 = never, 1 = where it is measured faster than the FP64 tensor pipe (D >= 128:
-  // profiles/exp_i8_r02*.jsonl; at D = 64 one slab per tile leaves the epilogue and the slicing pass exposed and DMMA
-  // wins), 2 = whenever the shapes allow
+  // option i8_power: 0 = never (FP64 tensor pipe, DMMA), 1 / 2 = whenever the shapes allow.  Measured
+  // (profiles/exp_i8_r02h.jsonl, algorithmic TFLOP/s, i8 vs DMMA): D = 64 21.6 vs 21.4, 128 38.2 vs 25.3, 256 61.4 vs 27.7.
   const int mode = option_get(OPT_I8_POWER);
-  if (!mode || (mode == 1 && D < 128)) return false;
+  if (!mode) return false;
   return D >= 64 && D % 64 == 0 && d >= 1 && (int64_t)d * D < (1 << 19) && N * d < ((int64_t)1 << 30);
 }
 
@@ -85,7 +84,7 @@ i8_scale_kernel(int64_t len, Z* __restrict__ r, const double* __restrict__ norm,
   for (int j = 0; j < n; ++j) s += norm[(size_t)blockIdx.x * n + j];
   const double a = rsqrt(s);
   Z* p = r + (size_t)blockIdx.x * len;
-  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) p[i] = p[i] * a;
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.y * blockDim.x) p[i] = p[i] * a;
 }
 static __global__ void i8_sum_partials_kernel(int64_t nb, const Z* __restrict__ part, int n, Z* __restrict__ out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +142,7 @@ int tm_power_i8(int d, int D, int64_t N, const void* A, const void* B, void* r_i
   };
   for (int it = 0; it < K; ++it)
     if (int rc = apply(r, it == 0 ? nullptr : Rt, it == 0 ? nullptr : nrm, nrm, it == K - 1 ? r : nullptr, Rt, nullptr, nullptr)) return rc;
-  if (K > 0) i8_scale_kernel<<<(unsigned)N, 256, 0, st>>>(DD, r, nrm, tiles2);
+  if (K > 0) i8_scale_kernel<<<dim3((unsigned)N, (unsigned)((DD + 4095) / 4096 < 64 ? (DD + 4095) / 4096 : 64)), 256, 0, st>>>(DD, r, nrm, tiles2);
   if (rayleigh) {
     CK(scratch.get(&Er, sizeof(Z) * N * DD));
     CK(scratch.get(&dots, sizeof(Z) * N * tiles2));

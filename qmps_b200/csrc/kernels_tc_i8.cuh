@@ -220,6 +220,20 @@ __device__ __forceinline__ void tmem_ld16_i(uint32_t taddr, int (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = (int)r[i];
 }
+// the same without the wait: several loads in flight, one tmem_ld_wait() before the values are used
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// exact int64 -> double for |x| < 2^51 without the conversion pipe
+__device__ __forceinline__ double ll2d(long long x) {
+  return __longlong_as_double(x + 0x4338000000000000ll) - 6755399441055744.0;
+}
 __device__ __forceinline__ void epi_bar8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major,
@@ -331,7 +345,7 @@ zgemm_i8_kernel(Params p) {
       const int64_t bz = tile / tiles_per;
       const int rem = (int)(tile - bz * tiles_per), rbx = rem / p.ncbY, cby = rem - rbx * p.ncbY;
       const int row = rbx * XROWS + i;
-      const double rs = exp2i(p.ex_x[(bz * M + row) * 2 + upper]);
+      const double rs = exp2i(p.ex_x[(bz * M + row) * 2 + upper] - 28);
       // column scales 2^ey of this tile, once per tile: s_cs[c] for Y re rows (c < 32) and im rows (c >= 32)
       epi_bar8();                              // everybody is done with the previous tile's s_cs / exchange buffer
       if (tid_e < 64) {
@@ -341,27 +355,30 @@ zgemm_i8_kernel(Params p) {
       mbar_wait(tfull_bar, accphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * h);
-      // acc[c], c < 16: (my X plane row) . (Y re row 16 h + c);  acc[16 + c]: . (Y im row 16 h + c); smallest level first
+      // acc[c], c < 16: (my X plane row) . (Y re row 16 h + c);  acc[16 + c]: . (Y im row 16 h + c).
+      // The six levels are combined EXACTLY in 64-bit integers first (three levels per integer, IMAD.WIDE), so an output
+      // costs two int64 -> double bit tricks and one DFMA instead of six conversions and six DFMAs:
+      //     sum_t v_t 2^-7(t+2) = 2^-28 (hi + lo 2^-21),  hi = v0 2^14 + v1 2^7 + v2,  lo = v3 2^14 + v4 2^7 + v5
       double acc[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+      for (int half = 0; half < 2; ++half) {
+        int v[NSL][16];
 #pragma unroll
-      for (int t = NSL - 1; t >= 0; --t) {
-        const double wgt = 1.0 / (double)(1ull << (7 * (t + 2)));
-        int v[16];
-        tmem_ld16_i(taddr + (uint32_t)t * 64u, v);
+        for (int t = 0; t < NSL; ++t) tmem_ld16_nowait(taddr + (uint32_t)t * 64u + (uint32_t)half * 32u, v[t]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = fma(i2d(v[c]), wgt, acc[c]);
-        tmem_ld16_i(taddr + (uint32_t)t * 64u + 32u, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[16 + c] = fma(i2d(v[c]), wgt, acc[16 + c]);
+        for (int c = 0; c < 16; ++c) {
+          const long long hi = (long long)v[0][c] * 16384 + ((long long)v[1][c] * 128 + (long long)v[2][c]);
+          const long long lo = (long long)v[3][c] * 16384 + ((long long)v[4][c] * 128 + (long long)v[5][c]);
+          acc[16 * half + c] = fma(ll2d(lo), 4.76837158203125e-07, ll2d(hi));        // 2^-21
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar);                 // this thread no longer reads the accumulators
       accphase ^= 1u;
       epi_bar8();                              // s_cs is complete
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { acc[c] *= rs * s_cs[16 * h + c]; acc[16 + c] *= rs * s_cs[32 + 16 * h + c]; }
+      for (int c = 0; c < 16; ++c) { acc[c] *= rs * s_cs[16 * h + c]; acc[16 + c] *= rs * s_cs[32 + 16 * h + c]; }   // rs carries the 2^-28
       // lower thread (Xr row): acc = [RR | RI];  upper thread (Xi row): acc = [IR | II]  (16 complex columns each).
       // lower keeps local columns 0..7 and gives RR, RI of columns 8..15; upper the other way round.
       // (static register indices on both sides of every select: a run-time offset would push acc[] to local memory)

@@ -321,7 +321,7 @@ def leg_power(torch, B, dev, D, peaks, cdt_name, scale=1.0, nprob=None):
     apps = N * (K + 1)
     flops = 32.0 * D ** 3
     achieved = apps * flops / ms * 1e3 / 1e12
-    i8 = cdt_name == "c128" and D >= 128 and D % 64 == 0           # qmps_tm_power's default dispatch (option i8_power = 1)
+    i8 = cdt_name == "c128" and D >= 64 and D % 64 == 0            # qmps_tm_power's default dispatch (option i8_power = 1)
     if i8:
         peak, pipe, kern = peaks.get("i8_tcgen05_tops") or 2.0 * (peaks.get("bf16_tflops") or 1620.5), "tcgen05 kind::i8 (TOP/s)", "zgemm_i8_kernel"
         issued, what = achieved * 21.0, "; 21 exact int8 slice products issued per algorithmic real product"
