@@ -42,6 +42,14 @@ def reduced():
     V1, V2 = haar(3, 4), haar(3, 4)
     BW.bw_evolve_cost(z(V1), z(V2), z(V1[::-1].copy()), z(V2[::-1].copy()), z(haar(1, 16)[0]), want_all=True)   # group kernel
     BW.bw_expectation(z(V1), z(V2), z(haar(1, 16)[0]))
+    # round 2: the D = 8 tensor-pipe elimination (panel / update hand-over through shared memory), the PXP scar cost
+    from qmps_b200 import represent as R, scars as SC
+    from qmps_b200.ground_state import Hamiltonian
+    B.env_exact(A=tensors(3, 8))                             # env_dmma_kernel<0, 2>
+    prog = R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(24)).program()
+    th = torch.from_numpy(rng.normal(size=(3, 24))).to(dev)
+    B.energy_theta(prog, th, Hamiltonian({'ZZ': -1, 'X': 0.7}).to_matrix(), coord=1, shifts=B.ROTO3_SHIFTS)   # ansatz + env_dmma_kernel<1, 2>
+    SC.scars_costs(rng.normal(size=(5, 4)), rng.normal(size=4), SC.W(0.325, 0.1))
     torch.cuda.synchronize()
     print("sanitize_driver (reduced) done")
 
@@ -100,6 +108,24 @@ def main():
             A, Bt = tensors(n, D).to(cdt), tensors(n, D).to(cdt)
             B.tm_power(A, Bt, 2)
     B.loschmidt_rate(np.linspace(0.1, 2.0, 9), 1.5, 0.2)
+    # round 2 entries
+    from qmps_b200 import scars as SC, tools as T
+    from scipy.stats import unitary_group
+    A2 = tensors(37, 2)
+    B.unpack_env(B.env_exact_packed(A=A2).cpu().numpy())
+    B.env_exact_packed_host(A2.cpu().numpy())
+    T.get_env_exact(unitary_group.rvs(4, random_state=3))
+    SC.scars_costs(rng.normal(size=(21, 4)), rng.normal(size=4), SC.W(0.325, 0.1))
+    SC.simulate_scars(0.05, 2, 0.325, np.array([0.9, 0.4, 0.7, 1.1]), n_gen=2, npop=64, n_bfgs=2)
+    hh = torch.from_numpy(H).to(dev)
+    for D, n in ((2, 5), (4, 3)):
+        At = tensors(n, D)
+        B.tdvp_dadt(At, hh)
+        B.tdvp_evolve(At, hh, 0.01, 2)
+    prog = R.ShallowFullStateTensor(2, np.zeros(15)).program()
+    W = torch.from_numpy(expm(-1j * H * 0.1)).to(dev)
+    B.loschmidt_trajectory(prog, torch.from_numpy(rng.normal(size=15)).to(dev), W, 2, n_gen=2, npop=64, n_bfgs=2)
+    B.zgemm_i8(rng.normal(size=(2, 64, 128)) + 1j * rng.normal(size=(2, 64, 128)), rng.normal(size=(2, 32, 128)) + 1j * rng.normal(size=(2, 32, 128)))
     torch.cuda.synchronize()
     print("sanitize_driver done")
 
