@@ -392,6 +392,20 @@ def run_ours(args):
                               "api": "qmps_energy_theta_host (rank 0's shard, pageable numpy buffers)", "n_gpus": 1}
             return res
         leg("cfg4", cfg4)
+        if world > 1:
+            # config 5 "batched across the GPUs": the N independent problems split over the ranks (strong scaling, no collective)
+            def cfg5_sharded(D, ntot):
+                nloc = max(1, ntot // world)
+                r5 = BL.leg_power(torch, B, dev, D, peaks, "c128", nprob=nloc, with_e2e=False)
+                t5 = torch.tensor([r5["ms_per_step"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+                ms5 = float(t5.item())
+                apps = nloc * world * 33
+                r5.update({"workload": f"power_method_D{D}_N{nloc * world}_K32_c128_sharded", "value": apps / ms5 * 1e3, "ms_per_step": ms5,
+                           "units_per_step": apps, "n_gpus": world, "scaling": "strong", "collective": "none (independent problems)"})
+                return r5
+            leg("cfg5_D64_sharded", lambda: cfg5_sharded(64, 512))
+            leg("cfg5_D256_sharded", lambda: cfg5_sharded(256, 32))
         if world == 1:
             def steady():
                 n24 = 1 << 24
