@@ -213,10 +213,15 @@ def run_ours(args):
     status = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     stream = torch.cuda.current_stream().cuda_stream
 
+    # argument tuples are built once: the timed loop is K calls of the C entry and nothing else on the host side
+    fn = lib.qmps_env_exact
+    argv = [(2, 2, N, A[b].data_ptr(), 0, 1, eta[b].data_ptr(), r[b].data_ptr(), C[b].data_ptr(), status[b].data_ptr(), L.C128)
+            for b in range(NBUF)]
+
     def launch(i, st):
-        b = i % NBUF
-        L.check(lib.qmps_env_exact(2, 2, N, A[b].data_ptr(), 0, 1, eta[b].data_ptr(), r[b].data_ptr(), C[b].data_ptr(),
-                                   status[b].data_ptr(), L.C128, st), "env_exact")
+        rc = fn(*argv[i % NBUF], st)
+        if rc:
+            L.check(rc, "env_exact")
 
     def step(i):
         launch(i, stream)
