@@ -420,6 +420,15 @@ def test_c_abi_argument_validation_without_a_device(built):
         (lib.qmps_bw_expectation(1, 1, 1, 1, 3, 1, 1, 1, L.C128, None), ERR_UNSUPPORTED, "2 or 4 qubits"),
         (lib.qmps_cgemm_c64_tc(1, 1, 60, 64, 32, 1, 1, 0, 1, None), ERR_UNSUPPORTED, "multiples of 64"),
         (lib.qmps_set_option(b"no_such_option", 1), ERR_ARG, "unknown option"),
+        # round-2 entries
+        (lib.qmps_scars_cost(4, 1, 2, 1, 1, 1, None, None, L.C128, None), ERR_ARG, "NC must be 1 or N"),
+        (lib.qmps_scars_cost(4, None, 1, None, None, None, None, None, L.C128, None), ERR_ARG, "scars_cost"),
+        (lib.qmps_scars_trajectory(None, None, 1, 1, 64, 0.1, 0, 1, None, None, L.C128, None), ERR_ARG, "scars_trajectory"),
+        (lib.qmps_env_exact_packed(3, None, 0, None, None), ERR_ARG, "env_exact_packed"),
+        (lib.qmps_env_exact_packed_host(3, None, 0, None, 0), ERR_ARG, "env_exact_packed_host"),
+        (lib.qmps_get_env_exact_host(3, 1, 1, 1, None, L.C128, 0), ERR_UNSUPPORTED, "unsupported D"),
+        (lib.qmps_get_env_exact_host(2, 1, None, None, None, L.C128, 0), ERR_ARG, "get_env_exact_host"),
+        (lib.qmps_zgemm_c128_i8(1, 64, 32, 64, None, None, 0, None, None), ERR_ARG, "zgemm_c128_i8"),
     ]
     for rc, want, msg in cases:
         assert rc == want, (rc, want, msg)
@@ -429,6 +438,10 @@ def test_c_abi_argument_validation_without_a_device(built):
     assert lib.qmps_tm_power(2, 64, 0, None, None, None, 4, None, L.C64, None) == 0
     assert lib.qmps_bw_evolve_cost(0, 1, None, None, 0, None, None, 1, None, None, None, None, None, None, L.C128, None) == 0
     assert lib.qmps_env_exact(2, 2, 0, None, 0, 1, None, None, None, None, L.C128, None) == 0
+    assert lib.qmps_scars_cost(0, None, 1, None, None, None, None, None, L.C128, None) == 0
+    assert lib.qmps_env_exact_packed(0, None, 0, None, None) == 0
+    assert lib.qmps_env_exact_packed_host(0, None, 0, None, 0) == 0
+    assert lib.qmps_get_env_exact_host(2, 0, None, None, None, L.C128, 0) == 0
 
 
 def test_torch_library_ops_registered_cuda_only(built):
