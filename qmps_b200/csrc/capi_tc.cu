@@ -9,18 +9,26 @@ namespace {
 
 typedef cx<float> C;
 
-int64_t image_bytes(int64_t nmat, int R, int K) {
-  return nmat * (int64_t)(R / tc::ROWS) * (K / tc::KS) * tc::SLAB_BYTES;
+// Image mode (option tc_presplit: -1 = by size, 0 / 1 force): fp32 images split into hi / lo in shared memory halve
+// the global traffic, which is what bounds small K (D = 64: +33 %); at large K the kernel is bound by shared-memory
+// operand bandwidth and the extra split traffic costs more than it saves (D = 256: -14 %), so there the images carry
+// both planes as in round 1 (profiles/configs5_r02*.jsonl).
+int presplit_for(int K) {
+  const int v = option_get(OPT_TC_PRESPLIT);
+  return v >= 0 ? (v != 0) : (K >= 192);
+}
+int64_t image_bytes(int64_t nmat, int R, int K, int presplit) {
+  return nmat * (int64_t)(R / tc::ROWS) * (K / tc::KS) * (presplit ? tc::SLAB_BYTES : tc::IMG_SLAB_BYTES);
 }
 
 int launch_pack(int64_t nmat, int R, int K, const C* in, int64_t mstride, int64_t rstride, int64_t kstride,
-                unsigned char* img, cudaStream_t st) {
+                unsigned char* img, int presplit, cudaStream_t st) {
   const int64_t total = nmat * (int64_t)R * K;
   if (total == 0) return 0;
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  tc::pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kstride, img);
+  tc::pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(nmat, R, K, in, mstride, rstride, kstride, img, presplit);
   CK(cudaGetLastError());
   return 0;
 }
@@ -52,12 +60,14 @@ int cgemm_c64_tc(int64_t batch, int nsum, int M, int N, int K, const void* X, co
   if (!tc_shape_ok(M, N, K) || nsum < 1) return fail(QMPS_ERR_UNSUPPORTED, "cgemm_c64_tc: M, N must be multiples of 64 and K of 32");
   if (batch * nsum > (int64_t)1 << 30) return fail(QMPS_ERR_UNSUPPORTED, "cgemm_c64_tc: batch too large");
   unsigned char *xi = nullptr, *yi = nullptr;
-  CK(malloc_async((void**)&xi, image_bytes(batch * nsum, M, K), st));
-  CK(malloc_async((void**)&yi, image_bytes(batch * nsum, N, K), st));
-  if (int rc = launch_pack(batch * nsum, M, K, (const C*)X, (int64_t)M * K, K, 1, xi, st)) return rc;
-  if (int rc = launch_pack(batch * nsum, N, K, (const C*)Y, (int64_t)N * K, K, 1, yi, st)) return rc;
+  const int ps = presplit_for(K);
+  CK(malloc_async((void**)&xi, image_bytes(batch * nsum, M, K, ps), st));
+  CK(malloc_async((void**)&yi, image_bytes(batch * nsum, N, K, ps), st));
+  if (int rc = launch_pack(batch * nsum, M, K, (const C*)X, (int64_t)M * K, K, 1, xi, ps, st)) return rc;
+  if (int rc = launch_pack(batch * nsum, N, K, (const C*)Y, (int64_t)N * K, K, 1, yi, ps, st)) return rc;
   tc::Params p;
   memset(&p, 0, sizeof(p));
+  p.presplit = ps;
   p.X = xi; p.Y = yi; p.nsum = nsum; p.nkb = K / tc::KS; p.nrbX = M / tc::ROWS; p.nrbY = N / tc::ROWS;
   p.y_div = 1; p.batch = (int)batch; p.conj_y = conj_y; p.a_div = 1; p.out_c = (C*)Cout;
   if (int rc = launch_tile(p, st)) return rc;
@@ -78,25 +88,28 @@ int tm_power_tc(int d, int D, int64_t N, const void* A, const void* B, void* r_i
   const int64_t DD = (int64_t)D * D;
   unsigned char *Ai = nullptr, *Bi = nullptr, *Ti = nullptr, *Ri = nullptr;
   float* nrm = nullptr; C* dots = nullptr;
-  CK(malloc_async((void**)&Ai, image_bytes(N * d, D, D), st));
-  CK(malloc_async((void**)&Bi, image_bytes(N * d, D, D), st));
-  CK(malloc_async((void**)&Ti, image_bytes(N * d, D, D), st));
-  CK(malloc_async((void**)&Ri, image_bytes(N, D, D), st));
+  const int ps = presplit_for(D);
+  CK(malloc_async((void**)&Ai, image_bytes(N * d, D, D, ps), st));
+  CK(malloc_async((void**)&Bi, image_bytes(N * d, D, D, ps), st));
+  CK(malloc_async((void**)&Ti, image_bytes(N * d, D, D, ps), st));
+  CK(malloc_async((void**)&Ri, image_bytes(N, D, D, ps), st));
   CK(malloc_async((void**)&nrm, sizeof(float) * N * tiles, st));
   C* r = (C*)r_io;
   // A_s[i][k]: rows i, K = k;  B_s[l][j]: rows l, K = j;  r^T: rows j, K = k  (element (row j, k) = r[k][j])
-  if (int rc = launch_pack(N * d, D, D, (const C*)A, DD, D, 1, Ai, st)) return rc;
-  if (int rc = launch_pack(N * d, D, D, (const C*)B, DD, D, 1, Bi, st)) return rc;
-  if (int rc = launch_pack(N, D, D, r, DD, 1, D, Ri, st)) return rc;
+  if (int rc = launch_pack(N * d, D, D, (const C*)A, DD, D, 1, Ai, ps, st)) return rc;
+  if (int rc = launch_pack(N * d, D, D, (const C*)B, DD, D, 1, Bi, ps, st)) return rc;
+  if (int rc = launch_pack(N, D, D, r, DD, 1, D, Ri, ps, st)) return rc;
   auto apply = [&](const float* norm_in, float* norm_out, C* out_c, const C* dot_with, C* dot_out) -> int {
     tc::Params p1;
     memset(&p1, 0, sizeof(p1));
+    p1.presplit = ps;
     p1.X = Ai; p1.Y = Ri; p1.nsum = 1; p1.nkb = nkb; p1.nrbX = nrb; p1.nrbY = nrb; p1.y_div = d;
     p1.batch = (int)(N * d); p1.conj_y = 0; p1.norm_in = norm_in; p1.n_in = tiles; p1.a_div = d;
     p1.out_img = Ti; p1.out_mode = 1; p1.out_nrb = nrb; p1.out_nkb = nkb;
     if (int rc = launch_tile(p1, st)) return rc;
     tc::Params p2;
     memset(&p2, 0, sizeof(p2));
+    p2.presplit = ps;
     p2.X = Ti; p2.Y = Bi; p2.nsum = d; p2.nkb = nkb; p2.nrbX = nrb; p2.nrbY = nrb; p2.y_div = 1;
     p2.batch = (int)N; p2.conj_y = 1; p2.a_div = 1; p2.norm_out = norm_out;
     p2.out_img = Ri; p2.out_mode = 2; p2.out_nrb = nrb; p2.out_nkb = nkb;

@@ -21,17 +21,21 @@
 // memory and forms  Cr = RR -+ II,  Ci = RI +- IR.
 //
 // Memory.  Operands live in global memory as "slab images": for every (matrix, row block of 64,
-// K slab of 32) two 16 KB planes (hi, lo), each laid out EXACTLY as the UMMA K-major
+// K slab of 32) ONE 16 KB plane of fp32 values laid out EXACTLY as the UMMA K-major
 // SWIZZLE_128B shared-memory tile (8-row x 128-byte atoms, 16-byte chunk c of row r stored at
 // chunk c ^ (r & 7), 1024 bytes between 8-row groups).  A slab therefore moves with ONE bulk
-// copy of the TMA engine (cp.async.bulk, 32 KB, mbarrier complete_tx) and needs no tensor map.
+// copy of the TMA engine (cp.async.bulk, 16 KB, mbarrier complete_tx) and needs no tensor map.
+// The hi / lo TF32 split happens in SHARED memory after the copy (four splitter warps, element-wise and in place,
+// so the swizzle is untouched): round 1 stored both planes in global memory and D = 64 was bound by that traffic
+// (2.6x the algorithmic bytes, profiles/ncu_tc_canon_r01e.txt).
 // The epilogue writes its result directly as the slab image the next stage reads (natural for
 // T, transposed for r'), so r never leaves the image form between applications.
 //
-// Kernel structure (persistent, warp-specialised, 192 threads, 1 CTA per SM):
-//     warp 0   lane 0: producer  -- bulk copies into a 2-stage ring (64 KB per stage)
+// Kernel structure (persistent, warp-specialised, 320 threads, 1 CTA per SM):
+//     warp 0   lane 0: producer  -- bulk copies (2 x 16 KB) into a 3-stage ring (64 KB per stage once split)
+//     warps 6-9      : splitter  -- fp32 plane -> hi (in place) + lo planes, fence.proxy.async, hand-over to the issuer
 //     warp 1   lane 0: MMA issuer -- 4 K-steps x 3 UMMAs per slab, tcgen05.commit frees the stage
-//     warps 2-5      : epilogue  -- tcgen05.ld, pair exchange, scale / split / store, norms
+//     warps 2-5      : epilogue  -- tcgen05.ld, pair exchange, scale / store, norms
 // Two TMEM accumulators (2 x 128 columns) let the epilogue of tile n overlap the MMAs of n + 1.
 #pragma once
 #include <cuda_runtime.h>
@@ -44,11 +48,12 @@ namespace tc {
 constexpr int ROWS = 64;                       // complex rows per operand block
 constexpr int KS = 32;                         // K elements per slab (= one 128-byte swizzle row)
 constexpr int PLANE_BYTES = 128 * 128;         // 128 plane rows x 128 B
-constexpr int SLAB_BYTES = 2 * PLANE_BYTES;    // hi + lo
+constexpr int IMG_SLAB_BYTES = PLANE_BYTES;    // a slab in GLOBAL memory: one fp32 plane (round 2: half the image traffic)
+constexpr int SLAB_BYTES = 2 * PLANE_BYTES;    // a slab in SHARED memory: hi + lo TF32 planes, split after the bulk copy
 constexpr int STAGE_BYTES = 2 * SLAB_BYTES;    // X slab + Y slab
 constexpr int NSTAGE = 3;                        // 3 x 64 KB in flight per CTA (D = 64 is bound by image traffic)
 constexpr int XCH_BYTES = 128 * 64 * 4;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                     // producer, MMA issuer, 4 epilogue warps, 4 splitter warps
 constexpr int TMEM_COLS = 256;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + XCH_BYTES + 1024;   // + slack for the 1024-byte alignment
 
@@ -72,7 +77,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // element (row, k) of matrix m is in[m * mstride + row * rstride + k * kstride]
 static __global__ void __launch_bounds__(256)
 pack_kernel(int64_t nmat, int R, int K, const cx<float>* __restrict__ in, int64_t mstride, int64_t rstride,
-            int64_t kstride, unsigned char* __restrict__ img) {
+            int64_t kstride, unsigned char* __restrict__ img, int presplit) {
   const int nrb = R / ROWS, nkb = K / KS;
   const int64_t total = nmat * (int64_t)R * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -82,14 +87,19 @@ pack_kernel(int64_t nmat, int R, int K, const cx<float>* __restrict__ in, int64_
     const int64_t m = q / R;
     const cx<float> z = in[m * mstride + row * rstride + k * kstride];
     const int rb = row / ROWS, i = row % ROWS, kb = k / KS, kk = k % KS;
-    unsigned char* base = img + (((m * nrb + rb) * nkb + kb) * (int64_t)SLAB_BYTES);
-    float hi, lo;
-    split_tf32(z.re, hi, lo);
-    *reinterpret_cast<float*>(base + img_off(i, kk)) = hi;
-    *reinterpret_cast<float*>(base + PLANE_BYTES + img_off(i, kk)) = lo;
-    split_tf32(z.im, hi, lo);
-    *reinterpret_cast<float*>(base + img_off(64 + i, kk)) = hi;
-    *reinterpret_cast<float*>(base + PLANE_BYTES + img_off(64 + i, kk)) = lo;
+    unsigned char* base = img + (((m * nrb + rb) * nkb + kb) * (int64_t)(presplit ? SLAB_BYTES : IMG_SLAB_BYTES));
+    if (presplit) {
+      float hi, lo;
+      split_tf32(z.re, hi, lo);
+      *reinterpret_cast<float*>(base + img_off(i, kk)) = hi;
+      *reinterpret_cast<float*>(base + PLANE_BYTES + img_off(i, kk)) = lo;
+      split_tf32(z.im, hi, lo);
+      *reinterpret_cast<float*>(base + img_off(64 + i, kk)) = hi;
+      *reinterpret_cast<float*>(base + PLANE_BYTES + img_off(64 + i, kk)) = lo;
+    } else {
+      *reinterpret_cast<float*>(base + img_off(i, kk)) = z.re;
+      *reinterpret_cast<float*>(base + img_off(64 + i, kk)) = z.im;
+    }
   }
 }
 
@@ -185,6 +195,8 @@ struct Params {
   const unsigned char* X;      // slab images, matrix index  bz * nsum + t
   const unsigned char* Y;      // slab images, matrix index (bz / y_div) * nsum + t
   int nsum, nkb, nrbX, nrbY, y_div, batch, conj_y;
+  int presplit;                // 1: global images hold hi + lo planes (32 KB per slab, no in-kernel split): the large-K mode
+
   const float* norm_in; int n_in, a_div;   // alpha = rsqrt(sum_j norm_in[(bz / a_div) * n_in + j]); nullptr -> 1
   float* norm_out;             // [bz][tile] partial sums of |C|^2 after alpha
   unsigned char* out_img;      // next-stage image of C (matrix index bz)
@@ -198,7 +210,7 @@ struct Params {
 static __global__ void __launch_bounds__(THREADS, 1)
 cgemm_tc_kernel(Params p) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t s_bar[2 * NSTAGE + 4];
+  __shared__ __align__(8) uint64_t s_bar[3 * NSTAGE + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_red[4][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,9 +222,10 @@ cgemm_tc_kernel(Params p) {
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 4 + s); };   // the splitter warps are done with stage s
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
     fence_barrier_init();
   }
@@ -234,12 +247,13 @@ cgemm_tc_kernel(Params p) {
         const int rem = (int)(tile - bz * tiles_per), rbx = rem / p.nrbY, rby = rem - rbx * p.nrbY;
         for (int it = 0; it < iters; ++it) {
           const int t = it / p.nkb, kb = it - t * p.nkb;
-          const unsigned char* xs = p.X + ((((bz * p.nsum + t) * p.nrbX + rbx) * p.nkb + kb) * (int64_t)SLAB_BYTES);
-          const unsigned char* ys = p.Y + (((((bz / p.y_div) * p.nsum + t) * p.nrbY + rby) * p.nkb + kb) * (int64_t)SLAB_BYTES);
+          const int isb = p.presplit ? SLAB_BYTES : IMG_SLAB_BYTES;
+          const unsigned char* xs = p.X + ((((bz * p.nsum + t) * p.nrbX + rbx) * p.nkb + kb) * (int64_t)isb);
+          const unsigned char* ys = p.Y + (((((bz / p.y_div) * p.nsum + t) * p.nrbY + rby) * p.nkb + kb) * (int64_t)isb);
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          bulk_g2s(ring + stage * STAGE_BYTES, xs, SLAB_BYTES, full_bar(stage));
-          bulk_g2s(ring + stage * STAGE_BYTES + SLAB_BYTES, ys, SLAB_BYTES, full_bar(stage));
+          mbar_expect_tx(full_bar(stage), 2 * isb);
+          bulk_g2s(ring + stage * STAGE_BYTES, xs, isb, full_bar(stage));                 // fp32 plane: lands where hi will be
+          bulk_g2s(ring + stage * STAGE_BYTES + SLAB_BYTES, ys, isb, full_bar(stage));
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
@@ -254,7 +268,7 @@ cgemm_tc_kernel(Params p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
         for (int it = 0; it < iters; ++it) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(p.presplit ? full_bar(stage) : conv_bar(stage), phase);
           tc_fence_after();
           const uint32_t xs = ring + stage * STAGE_BYTES, ys = xs + SLAB_BYTES;
 #pragma unroll
@@ -274,6 +288,34 @@ cgemm_tc_kernel(Params p) {
       }
     }
     __syncwarp();
+  } else if (warp >= 6) {
+    // splitter warps: the bulk copy delivered fp32 planes; split every element x = hi + lo (TF32) in place -- hi stays
+    // where it landed, lo goes to the plane behind it -- then hand the stage to the MMA issuer.  Element-wise, so the
+    // SWIZZLE_128B layout is preserved.
+    const int tcv = threadIdx.x - 192;         // 0 .. 127
+    unsigned char* ring_g = smem_dyn + (ring - dyn0);
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total && !p.presplit; tile += gridDim.x) {
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar(stage), phase);
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          float4* hi4 = reinterpret_cast<float4*>(ring_g + stage * STAGE_BYTES + op * SLAB_BYTES);
+          float4* lo4 = reinterpret_cast<float4*>(ring_g + stage * STAGE_BYTES + op * SLAB_BYTES + PLANE_BYTES);
+#pragma unroll
+          for (int j = 0; j < PLANE_BYTES / 16 / 128; ++j) {
+            const int idx = tcv + 128 * j;
+            const float4 x = hi4[idx];
+            float4 h, l;
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+            hi4[idx] = h; lo4[idx] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(conv_bar(stage));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else {
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int prow = 32 * q + lane;            // plane row = TMEM lane
@@ -350,37 +392,51 @@ cgemm_tc_kernel(Params p) {
       }
       if (p.out_img && p.out_mode == 1) {
         // rows = C rows (block rbx), K = C columns: my 32 columns are exactly K slab 2*rby + upper
-        unsigned char* base = p.out_img + ((((bz * p.out_nrb + rbx) * p.out_nkb) + 2 * rby + upper) * (int64_t)SLAB_BYTES);
+        unsigned char* base = p.out_img + ((((bz * p.out_nrb + rbx) * p.out_nkb) + 2 * rby + upper) * (int64_t)(p.presplit ? SLAB_BYTES : IMG_SLAB_BYTES));
         unsigned char* rre = base + (i >> 3) * 1024 + (i & 7) * 128;
         unsigned char* rim = rre + 8 * 1024;                 // plane row 64 + i
+        if (p.presplit) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int pos = ((g ^ i) & 7) << 4;
-          float h[4], l[4];
+          for (int g = 0; g < 8; ++g) {
+            const int pos = ((g ^ i) & 7) << 4;
+            float h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(a[4 * g + e], h[e], l[e]);
-          *reinterpret_cast<float4*>(rre + pos) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(rre + PLANE_BYTES + pos) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int e = 0; e < 4; ++e) split_tf32(a[4 * g + e], h[e], l[e]);
+            *reinterpret_cast<float4*>(rre + pos) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(rre + PLANE_BYTES + pos) = make_float4(l[0], l[1], l[2], l[3]);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(b[4 * g + e], h[e], l[e]);
-          *reinterpret_cast<float4*>(rim + pos) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(rim + PLANE_BYTES + pos) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int e = 0; e < 4; ++e) split_tf32(b[4 * g + e], h[e], l[e]);
+            *reinterpret_cast<float4*>(rim + pos) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(rim + PLANE_BYTES + pos) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int pos = ((g ^ i) & 7) << 4;
+            *reinterpret_cast<float4*>(rre + pos) = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+            *reinterpret_cast<float4*>(rim + pos) = make_float4(b[4 * g], b[4 * g + 1], b[4 * g + 2], b[4 * g + 3]);
+          }
         }
       } else if (p.out_img && p.out_mode == 2) {
         // rows = C columns (block rby), K = C rows: my row i sits at k = i & 31 of K slab 2*rbx + (i >> 5)
-        unsigned char* base = p.out_img + ((((bz * p.out_nrb + rby) * p.out_nkb) + 2 * rbx + (i >> 5)) * (int64_t)SLAB_BYTES);
+        unsigned char* base = p.out_img + ((((bz * p.out_nrb + rby) * p.out_nkb) + 2 * rbx + (i >> 5)) * (int64_t)(p.presplit ? SLAB_BYTES : IMG_SLAB_BYTES));
         const int k = i & 31;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int n = 32 * upper + c;
-          float h, l;
-          split_tf32(a[c], h, l);
           const uint32_t ore = img_off(n, k), oim = img_off(64 + n, k);
-          *reinterpret_cast<float*>(base + ore) = h;
-          *reinterpret_cast<float*>(base + PLANE_BYTES + ore) = l;
-          split_tf32(b[c], h, l);
-          *reinterpret_cast<float*>(base + oim) = h;
-          *reinterpret_cast<float*>(base + PLANE_BYTES + oim) = l;
+          if (p.presplit) {
+            float h, l;
+            split_tf32(a[c], h, l);
+            *reinterpret_cast<float*>(base + ore) = h;
+            *reinterpret_cast<float*>(base + PLANE_BYTES + ore) = l;
+            split_tf32(b[c], h, l);
+            *reinterpret_cast<float*>(base + oim) = h;
+            *reinterpret_cast<float*>(base + PLANE_BYTES + oim) = l;
+          } else {
+            *reinterpret_cast<float*>(base + ore) = a[c];
+            *reinterpret_cast<float*>(base + oim) = b[c];
+          }
         }
       }
       if (p.norm_out || p.dot_out) {
