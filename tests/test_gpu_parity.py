@@ -151,6 +151,59 @@ def test_env_generic_vs_oracle(env, D, count, lc):
         assert np.abs(res.C[k].cpu().numpy() - C0).max() < 100 * tol
 
 
+def test_env_d8_tensor_pipe_kernel_edge_cases(env):
+    """The D = 8 blocked elimination on the FP64 tensor pipe (env_dmma_kernel, the complex128 default) against the
+    row-per-thread kernel it replaced and the oracle: Haar tensors, ansatz tensors at theta = 0 and at a small angle
+    (environments with tiny Schmidt values), a product state (singular fixed-point system), d = 1, 3, 4 (the
+    run-time physical-dimension build), and a batch that is not a multiple of anything."""
+    t, B, O, L, R = env["torch"], env["B"], env["O"], env["L"], env["R"]
+    lib = L.load()
+    rng = np.random.default_rng(88)
+    cases = []
+    cases.append(tensors(8, 37, 808, O))
+    prog = R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(24)).program()
+    th = np.concatenate([np.zeros((1, 24)), 1e-3 * rng.normal(size=(3, 24)), rng.normal(size=(9, 24))])
+    cases.append(B.ansatz_tensors(prog, t.from_numpy(th).cuda()).cpu().numpy())
+    for d in (1, 3, 4):                                       # left-canonical tensors with another physical dimension
+        Z = rng.normal(size=(5, d * 8, 8)) + 1j * rng.normal(size=(5, d * 8, 8))
+        if d == 1:
+            Q = np.stack([np.linalg.qr(z)[0] for z in Z])     # unitary 8 x 8: r = 1/8 exactly
+        else:
+            Q = np.stack([np.linalg.qr(z)[0] for z in Z])
+        cases.append(np.ascontiguousarray(Q.reshape(5, 8, d, 8).transpose(0, 2, 1, 3)))
+    for A in cases:
+        Ad = t.from_numpy(np.ascontiguousarray(A)).cuda()
+        outs = {}
+        for v in (3, 0):
+            lib.qmps_set_option(b"er_wide", v)
+            try:
+                outs[v] = B.env_exact(A=Ad)
+                t.cuda.synchronize()
+            finally:
+                lib.qmps_set_option(b"er_wide", -1)
+        st3, st0 = outs[3].status.cpu().numpy(), outs[0].status.cpu().numpy()
+        ok = (st3 == 0) & (st0 == 0)
+        # the two kernels may disagree on the status only where the system is singular to rounding (d = 1: r is not unique)
+        if A.shape[1] > 1:
+            assert np.array_equal(st3 != 0, st0 != 0)
+        r3, r0 = outs[3].r.cpu().numpy(), outs[0].r.cpu().numpy()
+        for k in np.nonzero(ok)[0]:
+            if A.shape[1] == 1:
+                continue
+            gap = min(1.0, gap_of(A[k], O))
+            assert np.abs(r3[k] - r0[k]).max() < 10 * TOL / gap
+            _, rr, CC, _ = O.env_exact_parts(A[k])
+            assert np.abs(r3[k] - rr).max() < 10 * TOL / gap
+            assert abs(np.trace(r3[k]) - 1) < 1e-12 and np.abs(r3[k] - r3[k].conj().T).max() == 0
+            if np.linalg.eigvalsh(rr)[0] > 1e-9:
+                assert np.abs(outs[3].C[k].cpu().numpy() - CC).max() < 1000 * TOL / gap / np.sqrt(np.linalg.eigvalsh(rr)[0])
+    # a product state: Phi(r) = r has a degenerate solution space -> flagged, not a silent wrong answer
+    Ap = np.zeros((1, 2, 8, 8), dtype=complex)
+    Ap[0, 0] = np.eye(8)
+    res = B.env_exact(A=t.from_numpy(Ap).cuda())
+    assert int(res.status[0]) in (L.ST_SINGULAR, L.ST_NOT_PD)
+
+
 def test_env_general_tensor_not_canonical(env):
     t, B, O = env["torch"], env["B"], env["O"]
     rng = np.random.default_rng(4)
