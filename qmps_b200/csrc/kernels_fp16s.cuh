@@ -433,12 +433,16 @@ fp16s8_kernel(FpParams p) {
       // left phase.  Column q is carried in pa (rows <= 8 only), column q + 8 in pb.
       {
         cx<T> pa = S[F16S(lo < 8 ? lo : 8, q)], pb = S[F16S(lo, q8)];
+        // next row's entries of my two columns, loaded one rotation ahead (row i is not written before rotation i + 1)
+        cx<T> qa = mk<T>(0, 0), qb = S[F16S(lo + 1 <= hi ? lo + 1 : hi, q8)];
+        if (lo + 1 <= 8) qa = S[F16S(lo + 1 <= hi ? lo + 1 : hi, q)];
 #pragma unroll 1
         for (int i = lo + 1; i <= hi; ++i) {
           const bool low = i <= 8;                           // uniform: column q still has entries in rows (i-1, i)
-          cx<T> qa = mk<T>(0, 0);
-          if (low) qa = S[F16S(i, q)];
-          const cx<T> qb = S[F16S(i, q8)];
+          const int in = i + 1 <= hi ? i + 1 : hi;
+          cx<T> qa_n = mk<T>(0, 0);
+          if (in <= 8) qa_n = S[F16S(in, q)];
+          const cx<T> qb_n = S[F16S(in, q8)];
           const bool act = busy && (i > lw) && (i <= enw);
           const cx<T> f = low ? pa : pb, g = low ? qa : qb;  // column i-1 is an "a" column iff i-1 < 8
           const T nr2 = norm2(f) + norm2(g);
@@ -447,12 +451,12 @@ fp16s8_kernel(FpParams p) {
           cx<T> c = f * inr, s = g * inr;
           const T nr = nr2 * inr;
           const bool owner = q == ((i - 1) & 7);
-          if (owner) {
-            if (ok) { rot[2 * i] = c; rot[2 * i + 1] = s; }
-            else { rot[2 * i] = mk<T>(1, 0); rot[2 * i + 1] = mk<T>(0, 0); }
-          }
-          __syncwarp();
-          c = rot[2 * i]; s = rot[2 * i + 1];
+          if (!ok) { c = mk<T>(1, 0); s = mk<T>(0, 0); }
+          if (owner) { rot[2 * i] = c; rot[2 * i + 1] = s; }   // for the right phase (read after the __syncwarp below the loop)
+          // the rotation from its owner lane by shuffles: no shared-memory round trip on the critical path
+          const int src = (i - 1) & 7;
+          c.re = __shfl_sync(0xffffffffu, c.re, src, 8); c.im = __shfl_sync(0xffffffffu, c.im, src, 8);
+          s.re = __shfl_sync(0xffffffffu, s.re, src, 8); s.im = __shfl_sync(0xffffffffu, s.im, src, 8);
           cx<T> top = conj(c) * pb; cmad(top, conj(s), qb);
           cx<T> bot = c * qb; cmsub(bot, s, pb);
           if (low) {
@@ -464,6 +468,7 @@ fp16s8_kernel(FpParams p) {
           } else if (ok && owner) { top = mk<T>(nr, 0); bot = mk<T>(0, 0); }
           S[F16S(i - 1, q8)] = top;
           pb = bot;
+          qa = qa_n; qb = qb_n;
         }
         if (lo < 8) S[F16S(hi < 8 ? hi : 8, q)] = pa;
         S[F16S(hi, q8)] = pb;
