@@ -10,6 +10,8 @@ Shapes: tensors ``A[..., d, D, D]`` with ``A[s, i, j]`` as produced by
 """
 from collections import namedtuple
 
+import collections
+
 import numpy as np
 import torch
 
@@ -472,8 +474,43 @@ def expectation_values(A, ops, r=None, lvec=None, eta=None, assume_left_canonica
 
 def overlap(A, B):
     """``iMPS.overlap`` as the reference plots it: per-site fidelity |eta(E_AB)|^2
-    for batches of tensors (broadcast like ``fixed_point``)."""
+    for batches of tensors (broadcast like ``fixed_point``).  D <= 16: dense eigen-solve of the mixed transfer matrix;
+    larger D: its leading eigenvalue by the power method on the tensor-core contraction (``overlap_power``)."""
+    D = A.shape[-1]
+    if D > 16:
+        return overlap_power(A, B).fid
     return fixed_point(A, B, want_vec=False, want_status=False).fid
+
+
+PowerOverlap = collections.namedtuple("PowerOverlap", "eta fid rate r iterations converged")
+
+
+def overlap_power(A, B, tol=1e-10, chunk=32, max_iter=8192):
+    """Leading eigenvalue eta of the mixed transfer matrix E_AB at LARGE bond dimension (D >= 64 runs on tcgen05) by
+    the power method r <- sum_s A_s r B_s^dagger / |.|: the Loschmidt-echo / overlap step of a classical iMPS
+    (``A_.overlap(A)``, ``Trajectory.loschmidts()``; qmps/loschmidts/time_evo.py:145, mps_loschmidts.py:20-22) where a
+    dense D^2 x D^2 eigen-solve is out of reach.  Runs ``chunk`` applications per C-ABI call (``qmps_tm_power``) and
+    stops when every problem's Rayleigh quotient moved by less than ``tol`` (relative) over a chunk (the exact-integer
+    complex128 contraction is good to ~4e-12 per application, so tolerances below ~1e-11 cannot be met).
+    Returns ``PowerOverlap(eta[N], fid = |eta|^2, rate = -log|eta|^2, r[N, D, D], iterations, converged[N])``."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    B = _cdev(B, A.dtype, A.device)
+    if A.shape != B.shape:
+        raise ValueError("overlap_power needs A and B of the same shape [N, d, D, D]")
+    r, prev, it = None, None, 0
+    conv = None
+    while it < max_iter:
+        r, ray = tm_power(A, B, chunk, r0=r)
+        it += chunk
+        if prev is not None:
+            conv = (ray - prev).abs() <= tol * ray.abs().clamp_min(1e-300)
+            if bool(conv.all()):
+                break
+        prev = ray
+    if conv is None:
+        conv = torch.zeros(ray.shape, dtype=torch.bool, device=ray.device)
+    a2 = (ray.real ** 2 + ray.imag ** 2)
+    return PowerOverlap(ray, a2, -torch.log(a2), r, it, conv)
 
 
 # ---- a13 -----------------------------------------------------------------------------

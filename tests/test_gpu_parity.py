@@ -598,6 +598,38 @@ def test_tm_power_vs_oracle(env, D):
         assert abs(ray[k].item() - q0) < 1e-12
 
 
+@pytest.mark.parametrize("D", [64, 128])
+def test_overlap_power_large_D_vs_sparse_eigensolver(env, D):
+    """Large-D Loschmidt-echo / overlap step: the leading eigenvalue of E_AB from the power method on the tensor-core
+    contraction against ARPACK on the same map applied as a linear operator (a dense D^2 x D^2 eig is out of reach)."""
+    from scipy.sparse.linalg import LinearOperator, eigs
+    t, B, O = env["torch"], env["B"], env["O"]
+    cnt = 3
+    A = tensors(D, cnt, 9100 + D, O)
+    rng = np.random.default_rng(D)
+    # B = A moved by a small unitary rotation of the physical index and a perturbation: a well-gapped, complex eta
+    Bt = np.empty_like(A)
+    for k in range(cnt):
+        Z = A[k].transpose(1, 0, 2).reshape(2 * D, D) + 0.01 * (rng.normal(size=(2 * D, D)) + 1j * rng.normal(size=(2 * D, D))) / np.sqrt(D)
+        Uz, _, Vz = np.linalg.svd(Z, full_matrices=False)       # closest isometry (polar factor): stays in A's gauge
+        Q = (Uz @ Vz) * np.exp(0.3j)
+        Bt[k] = Q.reshape(D, 2, D).transpose(1, 0, 2)
+    res = B.overlap_power(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda(), tol=1e-10)
+    assert bool(res.converged.all()) and res.iterations <= 2048
+    eta = res.eta.cpu().numpy()
+    for k in range(cnt):
+        Bh = Bt[k].conj().transpose(0, 2, 1)
+        op = LinearOperator((D * D, D * D), dtype=complex,
+                            matvec=lambda v: np.sum(A[k] @ v.reshape(D, D) @ Bh, axis=0).reshape(-1))
+        ref = eigs(op, k=1, which="LM", tol=1e-13)[0][0]
+        assert abs(eta[k] - ref) < 1e-8 * abs(ref)
+        rk = res.r[k].cpu().numpy()
+        assert np.abs(np.sum(A[k] @ rk @ Bh, axis=0) - eta[k] * rk).max() < 1e-6       # eigen-equation residual
+    fid = B.overlap(t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()).cpu().numpy()      # dispatches to the power method for D > 16
+    assert np.abs(fid - np.abs(eta) ** 2).max() < 1e-9
+    assert np.abs(res.rate.cpu().numpy() + np.log(np.abs(eta) ** 2)).max() < 1e-12
+
+
 def test_tm_power_same_tensor_converges_to_environment(env):
     """Size-independent property: for A = B left-canonical the power method converges to the
     exact environment of the direct solver (trace-normalised), Rayleigh quotient -> 1."""
