@@ -348,17 +348,23 @@ def loschmidt_costs(program, theta, A0, W, dtype=torch.complex128, want_status=F
     return (cost, echo, eta, st) if want_status else (cost, echo, eta)
 
 
-def loschmidt_costs_host(program, theta, A0, W, dtype=np.complex128, device=0, want_echo=True):
+def loschmidt_costs_host(program, theta, A0, W, dtype=np.complex128, device=0, want_echo=True, out_cost=None, out_echo=None):
     """``loschmidt_costs`` on HOST arrays through ``qmps_loschmidt_batched_host`` (numpy in, numpy out; the
-    copies are part of the call): theta[NP, P] float64, A0[2, D, D], W[NT, 4, 4] -> cost[NP, NT] (, echo)."""
+    copies are part of the call): theta[NP, P] float64, A0[2, D, D], W[NT, 4, 4] -> cost[NP, NT] (, echo).
+    ``out_cost`` / ``out_echo``: caller-owned result arrays, e.g. views of PINNED memory
+    (``torch.empty(..., pin_memory=True).numpy()``) -- the 16 NT bytes per parameter set that come back then move at
+    the link rate instead of the pageable-copy rate."""
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     A0 = np.ascontiguousarray(A0, dtype=dtype)
     W = np.ascontiguousarray(W, dtype=dtype).reshape(-1, 4, 4)
     NP, P = theta.shape
     NT = W.shape[0]
     rd = np.float64 if np.dtype(dtype) == np.complex128 else np.float32
-    cost = np.empty((NP, NT), dtype=rd)
-    echo = np.empty((NP, NT), dtype=rd) if want_echo else None
+    cost = np.empty((NP, NT), dtype=rd) if out_cost is None else out_cost
+    echo = (np.empty((NP, NT), dtype=rd) if out_echo is None else out_echo) if want_echo else None
+    for o in (cost, echo):
+        if o is not None and (o.shape != (NP, NT) or o.dtype != rd or not o.flags.c_contiguous):
+            raise ValueError("out_cost / out_echo must be C-contiguous [NP, NT] arrays of the real type of dtype")
     ops = program.c_ops()
     L.check(L.require_device().qmps_loschmidt_batched_host(
         ops, len(program), program.nq, NP, P, theta.ctypes.data, A0.ctypes.data, NT, W.ctypes.data, cost.ctypes.data,
