@@ -56,11 +56,13 @@ def energy_density(AL, h, r=None):
     return float(np.einsum("stji,stjk,ki->", AA.conj(), C, r).real)
 
 
-def tdvp_tangent_left_canonical(AL, h, imaginary=False):
+def tdvp_tangent_left_canonical(AL, h, imaginary=False, r=None):
     """(dA_L/dt, e) for a LEFT-CANONICAL tensor A_L[d, D, D] and a two-site Hamiltonian h[d*d, d*d];
-    ``imaginary``: the imaginary-time flow (-1 instead of -i)."""
+    ``imaginary``: the imaginary-time flow (-1 instead of -i).  ``r``: the Hermitian trace-1 right fixed point if the
+    caller already has it (large D: a dense D^2 x D^2 eig is slow, an iterative eigen-solver supplies it)."""
     d, D, _ = AL.shape
-    _, _, r = eigs(AL)                                             # Hermitian, trace 1
+    if r is None:
+        _, _, r = eigs(AL)                                         # Hermitian, trace 1
     AA = np.einsum("sij,tjk->stik", AL, AL)
     C = np.einsum("abcd,cdik->abik", np.asarray(h, dtype=complex).reshape(d, d, d, d), AA)
     Hl = np.einsum("stji,stjk->ik", AA.conj(), C)

@@ -580,6 +580,12 @@ def tdvp_dadt(A, h, imaginary=False, assume_left_canonical=False, want_status=Fa
     Returns (dA[N, d, D, D], energy[N]) (+ status)."""
     A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
     N, d, D, _ = A.shape
+    if D > 16:                                   # large bond dimension: composed from the tensor-core contraction kernels
+        if not assume_left_canonical:
+            raise NotImplementedError("tdvp_dadt at D > 16 needs a left-canonical tensor (assume_left_canonical=True)")
+        dA, e, _ = tdvp_tangent_large(A, h, imaginary=imaginary)
+        st = torch.zeros((N,), dtype=torch.int32, device=A.device)
+        return (dA, e, st) if want_status else (dA, e)
     hd = _cdev(h, A.dtype, A.device).reshape(d * d, d * d).contiguous()
     dA = torch.empty_like(A)
     e = torch.empty((N,), dtype=_RDT[A.dtype], device=A.device)
@@ -588,6 +594,75 @@ def tdvp_dadt(A, h, imaginary=False, assume_left_canonical=False, want_status=Fa
     with torch.cuda.device(A.device):
         L.check(fn(d, D, N, _p(A), _p(hd), int(bool(imaginary)), _p(dA), _p(e), _p(st), _dt(A), _stream()), "tdvp_dadt")
     return (dA, e, st) if want_status else (dA, e)
+
+
+def tdvp_tangent_large(AL, h, imaginary=False, tol=1e-11, chunk=32, max_iter=4096):
+    """The TDVP tangent vector of LEFT-CANONICAL tensors at LARGE bond dimension (D a multiple of 64, complex128):
+    ``iMPS([A]).dA_dt([h])`` (scripts/classical_time_evolution.py:22-26) where the D^2 x D^2 systems of
+    ``qmps_tdvp_tangent`` (D <= 16) are out of reach.  Same formulas as ``csrc/tdvp.cuh`` / ``oracle/tdvp.py``, with every
+    O(D^3) contraction on the tcgen05 ``kind::i8`` kernels (``qmps_tm_power`` for the fixed point r, ``qmps_zgemm_c128_i8``
+    for the products) and the two linear solves as iterations of the transfer map:
+        r          power method (chunks of ``chunk`` applications until the Rayleigh quotient is stationary to ``tol``)
+        K          the Neumann series K = sum_n E_L^n (H_l - e), E_L(K) = sum_s A_s^dagger K A_s (the right-hand side has no
+                   component along the fixed point, so the series converges like |lambda_2|^n); stopped at ``tol``.
+    This is a HOST-LEVEL COMPOSITION: the O(D^2) glue (transposes, axpy, traces, the d^2 x d^2 contraction with h) and the
+    D x D inverse of r (``torch.linalg.inv``, a library call) go through torch; the tensor-core kernels do the rest.
+    Returns (dA[N, d, D, D], energy[N], info) with info = dict(r_iterations, k_iterations, r)."""
+    AL = _cdev(AL, torch.complex128)
+    N, d, D, _ = AL.shape
+    if D % 64:
+        raise ValueError("tdvp_tangent_large needs D % 64 == 0 (use tdvp_dadt for D <= 16)")
+    dev = AL.device
+    hd = _cdev(h, torch.complex128, dev).reshape(d, d, d, d)
+    T_ = lambda X: X.transpose(-1, -2).contiguous()                         # noqa: E731
+    H_ = lambda X: X.conj().transpose(-1, -2).contiguous()                   # noqa: E731
+
+    def mm(P, Q):                                                            # P . Q, batched over the leading dimensions
+        shp = P.shape[:-2]
+        return zgemm_i8(P.reshape(-1, D, D).contiguous(), T_(Q).reshape(-1, D, D)).reshape(*shp, D, D)
+    # fixed point r of r -> sum_s A_s r A_s^dagger (Hermitian, trace 1)
+    r, prev, it_r = None, None, 0
+    while it_r < max_iter:
+        r, ray = tm_power(AL, AL, chunk, r0=r)
+        it_r += chunk
+        if prev is not None and bool(((ray - prev).abs() <= tol).all()):
+            break
+        prev = ray
+    r = 0.5 * (r + H_(r))
+    tr = torch.einsum("nii->n", r)
+    r = r / tr[:, None, None]
+    r = 0.5 * (r + H_(r))
+    # two-site blocks and the left Hamiltonian
+    As = AL[:, :, None].expand(N, d, d, D, D)
+    At = AL[:, None, :].expand(N, d, d, D, D)
+    AA = mm(As, At)                                                          # AA[s, t] = A_s A_t
+    C = torch.einsum("abcd,ncdik->nabik", hd, AA).contiguous()              # C[a, b] = sum h[(a,b),(c,d)] AA[c, d]
+    Hl = mm(H_(AA), C).sum(dim=(1, 2))                                       # sum_st AA_st^dagger C_st
+    e = torch.einsum("nik,nki->n", Hl, r).real
+    eye = torch.eye(D, dtype=torch.complex128, device=dev)
+    Bm = Hl - e[:, None, None].to(torch.complex128) * eye
+    AH = H_(AL)                                                              # A_s^dagger
+    K, it_k = Bm.clone(), 0
+    while it_k < max_iter:
+        KA = mm(K[:, None].expand(N, d, D, D), AL)                           # K A_s
+        Kn = Bm + mm(AH, KA).sum(dim=1)
+        it_k += 1
+        delta = (Kn - K).abs().amax(dim=(1, 2))
+        K = Kn
+        if bool((delta <= tol * K.abs().amax(dim=(1, 2)).clamp_min(1e-300)).all()):
+            break
+    K = K - torch.einsum("nik,nki->n", K, r)[:, None, None] * eye            # tr(K r) = 0
+    rinv = torch.linalg.inv(r)
+    # G^s = sum_t C^{st} r A_t^dagger r^-1 + sum_t A_t^dagger C^{ts} + K A_s
+    Cr = mm(C, r[:, None, None].expand(N, d, d, D, D))                       # C^{st} r
+    Ar = mm(AH, rinv[:, None].expand(N, d, D, D))                            # A_t^dagger r^-1
+    G = mm(Cr, Ar[:, None].expand(N, d, d, D, D)).sum(dim=2)                 # sum_t (C^{st} r)(A_t^dagger r^-1)
+    G = G + mm(AH[:, :, None].expand(N, d, d, D, D), C).sum(dim=1)           # sum_t A_t^dagger C^{ts}  (index [t, s] summed over t)
+    G = G + mm(K[:, None].expand(N, d, D, D), AL)
+    P = mm(AH, G).sum(dim=1)                                                 # sum_u A_u^dagger G^u
+    f = -1.0 if imaginary else -1j
+    dA = f * (G - mm(AL, P[:, None].expand(N, d, D, D)))
+    return dA, e, dict(r_iterations=it_r, k_iterations=it_k, r=r)
 
 
 def tdvp_evolve(A, h, dt, n_steps, method="rk4", imaginary=False, want_traj=False, want_rates=True, want_energy=True):

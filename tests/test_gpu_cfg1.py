@@ -354,3 +354,31 @@ def test_loschmidt_trajectory_on_device(env, golden):
     assert (np.diff(rate[:20]) > 0).all()                                      # the echo decays monotonically at first
     assert (np.abs(rate[5:] - exact[5:]) < 0.02 * exact[5:]).all()            # (3) D = 2 follows the analytic curve to 2 %
     # (measured on a B200: rate 0.00750 0.02998 0.06721 0.11859 0.18297 at t = 5, 10, .., 25 dt; exact 0.00756 0.03014 0.06749 0.11907 0.18393)
+
+
+def test_tdvp_tangent_large_D_on_tensor_cores_vs_oracle(env):
+    """D = 64: the tangent vector composed from the tcgen05 contraction kernels (power method for r, Neumann series for
+    the left Hamiltonian, kind::i8 products) against the oracle's dense solve of the same equations, with r from ARPACK."""
+    from scipy.sparse.linalg import LinearOperator, eigs as sp_eigs
+    t, B, O = env["torch"], env["B"], env["O"]
+    D, N = 64, 2
+    rng = np.random.default_rng(64)
+    Z = rng.normal(size=(N, 2 * D, D)) + 1j * rng.normal(size=(N, 2 * D, D))
+    A = np.stack([np.linalg.qr(z)[0].reshape(D, 2, D).transpose(1, 0, 2) for z in Z])      # left-canonical
+    h = O.tfim_matrix(0.7)
+    dA, e, info = B.tdvp_tangent_large(t.from_numpy(A).cuda(), h)
+    dA, e = dA.cpu().numpy(), e.cpu().numpy()
+    assert info["k_iterations"] < 400 and info["r_iterations"] <= 1024
+    for k in range(N):
+        Ah = A[k].conj().transpose(0, 2, 1)
+        op = LinearOperator((D * D, D * D), dtype=complex, matvec=lambda v: np.sum(A[k] @ v.reshape(D, D) @ Ah, axis=0).reshape(-1))
+        w, v = sp_eigs(op, k=1, which="LM", tol=1e-13)
+        r = v[:, 0].reshape(D, D)
+        r = r / np.trace(r)
+        r = 0.5 * (r + r.conj().T)
+        assert np.abs(info["r"][k].cpu().numpy() - r).max() < 1e-9
+        d0, e0 = O.tdvp_tangent_left_canonical(A[k], h, r=r)
+        assert abs(e[k] - e0) < 1e-9
+        assert np.abs(dA[k] - d0).max() < 1e-7 * max(1.0, np.abs(d0).max())
+        # the tangent is in the left gauge: sum_s A_s^dagger dA_s = 0
+        assert np.abs(np.einsum("ski,skj->ij", A[k].conj(), dA[k])).max() < 1e-8
