@@ -581,9 +581,10 @@ def tdvp_dadt(A, h, imaginary=False, assume_left_canonical=False, want_status=Fa
     A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
     N, d, D, _ = A.shape
     if D > 16:                                   # large bond dimension: composed from the tensor-core contraction kernels
-        if not assume_left_canonical:
-            raise NotImplementedError("tdvp_dadt at D > 16 needs a left-canonical tensor (assume_left_canonical=True)")
-        dA, e, _ = tdvp_tangent_large(A, h, imaginary=imaginary)
+        if assume_left_canonical:
+            dA, e, _ = tdvp_tangent_large(A, h, imaginary=imaginary)
+        else:
+            dA, e = tdvp_dadt_large(A, h, imaginary=imaginary)
         st = torch.zeros((N,), dtype=torch.int32, device=A.device)
         return (dA, e, st) if want_status else (dA, e)
     hd = _cdev(h, A.dtype, A.device).reshape(d * d, d * d).contiguous()
@@ -665,11 +666,77 @@ def tdvp_tangent_large(AL, h, imaginary=False, tol=1e-11, chunk=32, max_iter=409
     return dA, e, dict(r_iterations=it_r, k_iterations=it_k, r=r)
 
 
+def left_canonicalise_large(A, tol=1e-11, chunk=32, max_iter=4096):
+    """``iMPS([A]).left_canonicalise()`` at large bond dimension (D % 64 == 0, complex128): l from the power method of the
+    left transfer map on the tensor-core contraction, L = chol(l) (``torch.linalg.cholesky``), A_L = L A L^-1 / sqrt(eta)
+    with the two products on ``qmps_zgemm_c128_i8``.  Returns (A_L, eta[N], L) as ``tdvp_canonical_parts`` of the oracle."""
+    A = _cdev(A, torch.complex128)
+    N, d, D, _ = A.shape
+    AH = A.conj().transpose(-1, -2).contiguous()
+    l, prev, it = None, None, 0
+    while it < max_iter:
+        l, ray = tm_power(AH, AH, chunk, r0=l)                              # l <- sum_s A_s^dagger l A_s
+        it += chunk
+        if prev is not None and bool(((ray - prev).abs() <= tol * ray.abs()).all()):
+            break
+        prev = ray
+    eta = ray.real
+    l = 0.5 * (l + l.conj().transpose(-1, -2))
+    l = l / torch.einsum("nii->n", l).real[:, None, None] * D
+    Lu = torch.linalg.cholesky(l).conj().transpose(-1, -2).contiguous()      # upper factor: l = L^dagger L
+    Li = torch.linalg.inv(Lu)
+
+    def mm(P, Q):
+        shp = P.shape[:-2]
+        return zgemm_i8(P.reshape(-1, D, D).contiguous(), Q.transpose(-1, -2).contiguous().reshape(-1, D, D)).reshape(*shp, D, D)
+    AL = mm(mm(Lu[:, None].expand(N, d, D, D), A), Li[:, None].expand(N, d, D, D)) / torch.sqrt(eta)[:, None, None, None]
+    return AL, eta, Lu
+
+
+def tdvp_dadt_large(A, h, imaginary=False):
+    """``iMPS([A]).dA_dt([h])`` in ANY gauge at large D: canonicalise, tangent in the left gauge, transform back
+    (dA = sqrt(eta) L^-1 dA_L L; the left gauge condition is covariant).  Returns (dA, energy)."""
+    AL, eta, Lu = left_canonicalise_large(A)
+    dAL, e, _ = tdvp_tangent_large(AL, h, imaginary=imaginary)
+    N, d, D, _ = AL.shape
+    Li = torch.linalg.inv(Lu)
+
+    def mm(P, Q):
+        shp = P.shape[:-2]
+        return zgemm_i8(P.reshape(-1, D, D).contiguous(), Q.transpose(-1, -2).contiguous().reshape(-1, D, D)).reshape(*shp, D, D)
+    dA = mm(mm(Li[:, None].expand(N, d, D, D), dAL), Lu[:, None].expand(N, d, D, D)) * torch.sqrt(eta)[:, None, None, None]
+    return dA, e
+
+
+def tdvp_evolve_large(A, h, dt, n_steps, imaginary=False):
+    """The reference's RK4 loop (scripts/classical_time_evolution.py:21-27: four ``dA_dt``, ``left_canonicalise`` after
+    the step) at large bond dimension, with ``Trajectory.loschmidts()`` (-log|eta(E_{A_t A_0})|^2 by ``overlap_power``)
+    and the energy per bond at the start of every step.  Returns ``TdvpRun(A_final, traj, rates, energy)``."""
+    A0 = left_canonicalise_large(A)[0]
+    cur = A0
+    traj, energy = [A0], []
+    for _ in range(int(n_steps)):
+        k1, e = tdvp_dadt_large(cur, h, imaginary)
+        k2, _ = tdvp_dadt_large(cur + (dt / 2) * k1, h, imaginary)
+        k3, _ = tdvp_dadt_large(cur + (dt / 2) * k2, h, imaginary)
+        k4, _ = tdvp_dadt_large(cur + dt * k3, h, imaginary)
+        cur = left_canonicalise_large(cur + (dt / 6) * (k1 + 2 * k2 + 2 * k3 + k4))[0]
+        traj.append(cur)
+        energy.append(e)
+    T = torch.stack(traj)
+    rates = torch.stack([overlap_power(a, A0).rate for a in traj])
+    return TdvpRun(cur, T, rates, torch.stack(energy) if energy else None, None)
+
+
 def tdvp_evolve(A, h, dt, n_steps, method="rk4", imaginary=False, want_traj=False, want_rates=True, want_energy=True):
     """``n_steps`` TDVP steps of size ``dt`` for a batch of states, one C-ABI call, no host round trip:
     ``method='rk4'`` is the reference's loop (scripts/classical_time_evolution.py:21-27), ``'euler'`` is
     ``Trajectory.eulerint`` (qmps/loschmidts/mps_loschmidts.py:22).  Returns ``TdvpRun(A_final, traj, rates, energy)``:
     rates[t, n] = -log|eta(E_{A_t A_0})|^2 (``Trajectory.loschmidts()``), energy[t, n] at the start of step t."""
+    if A.shape[-1] > 16:                         # large bond dimension: the composition on the tensor-core contraction kernels
+        if method != "rk4":
+            raise NotImplementedError("tdvp_evolve at D > 16 implements the reference's RK4 loop only")
+        return tdvp_evolve_large(A, h, dt, n_steps, imaginary=imaginary)
     A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128).clone()
     N, d, D, _ = A.shape
     hd = _cdev(h, A.dtype, A.device).reshape(d * d, d * d).contiguous()
