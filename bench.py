@@ -430,6 +430,7 @@ def run_ours(args):
             leg("cfg1_scalar", lambda: BL.leg_scalar_latency(torch, dev))
             leg("cfg7", lambda: BL.leg_loschmidt(torch, B, R, dev, 2, peaks, scale=args.sub_scale))
             leg("cfg3", lambda: BL.leg_loschmidt(torch, B, R, dev, 4, peaks, scale=args.sub_scale))
+            leg("f3_tdvp_large", lambda: BL.leg_tdvp_large(torch, B, dev, peaks))
             for D in (64, 256):
                 for tag in ("c128", "c64"):
                     leg(f"cfg5_D{D}_{tag}", lambda D=D, tag=tag: BL.leg_power(torch, B, dev, D, peaks, tag, scale=args.sub_scale))

@@ -382,3 +382,33 @@ def leg_scalar_latency(torch, dev):
             "max_abs_diff_first_column_moduli": err,
             "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "kernel": "env_d2_stream_kernel + env2u_kernel",
                          "note": "three launches + two PCIe copies + one synchronisation; nothing here is throughput-bound"}}
+
+
+def leg_tdvp_large(torch, B, dev, peaks, D=64, N=64):
+    """(f)-3 at large bond dimension: TDVP tangent vectors of N left-canonical D = 64 tensors, every O(D^3) contraction on the
+    tcgen05 kind::i8 kernels (batched.tdvp_tangent_large); unit = one tangent vector."""
+    g = torch.Generator(device=dev).manual_seed(64)
+    Z = torch.randn((N, 2 * D, D), dtype=torch.float64, device=dev, generator=g) + 1j * torch.randn((N, 2 * D, D), dtype=torch.float64, device=dev, generator=g)
+    Q, _ = torch.linalg.qr(Z)
+    A = Q.reshape(N, D, 2, D).permute(0, 2, 1, 3).contiguous()
+    h = torch.tensor(np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0])) * -1.0 + 0.7 * 0.5 * (np.kron([[0, 1], [1, 0]], np.eye(2)) + np.kron(np.eye(2), [[0, 1], [1, 0]])),
+                     dtype=torch.complex128, device=dev)
+    info = {}
+
+    def fn():
+        out = B.tdvp_tangent_large(A, h)
+        info.update(out[2])
+        return out
+    ms = timed_ms(torch, fn, reps=2, warm=1)
+    d = 2
+    gemms = 5 * d * d + 4 * d + 2 * d * info["k_iterations"] + 2 * d * (info["r_iterations"] + 1)
+    flops = gemms * 8.0 * D ** 3
+    ach = N * flops / ms * 1e3 / 1e12
+    peak = peaks.get("i8_tcgen05_tops") or 2.0 * (peaks.get("bf16_tflops") or 1620.5)
+    return {"cfg": 5, "workload": f"tdvp_tangent_D{D}_N{N}_c128 (classical iTDVP step on the tensor-core contraction)", "metric": "tdvp_tangents_per_sec",
+            "unit": "tangents/s", "dtype": "c128", "value": N / ms * 1e3, "ms_per_step": ms, "units_per_step": N,
+            "api": "batched.tdvp_tangent_large (host-level composition over qmps_tm_power / qmps_zgemm_c128_i8)",
+            "iterations": {"power_method_r": info["r_iterations"], "neumann_K": info["k_iterations"]},
+            "roofline": _roof("tensor", ach * 21.0, peak, "TOP/s", "zgemm_i8_kernel + slice_kernel",
+                              f"{flops:.4g} real flops ({gemms} complex D^3 products at the measured iteration counts); 21 int8 products issued per real product",
+                              note="tcgen05 kind::i8 (TOP/s); many small launches with host-side convergence checks: latency, not the tensor pipe, bounds it")}
