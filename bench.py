@@ -391,10 +391,10 @@ def run_ours(args):
                 dist.all_reduce(t4, op=dist.ReduceOp.MAX)
             res = BL.finish_energy_d8(torch, B, raw, float(t4.item()), world, peaks)
             if rank == 0:
-                th = raw["theta_h"]
+                th = torch.from_numpy(raw["theta_h"]).pin_memory().numpy()      # the caller's parameter vectors in pinned host memory
                 ms_e = BL.wall_ms(lambda: B.energy_theta_host(raw["prog"], th, raw["H"], coord=5, shifts=B.ROTO3_SHIFTS, device=local_rank), reps=2, warm=1)
                 res["e2e"] = {"value": 3 * len(th) / ms_e * 1e3, "unit": "evals/s", "h2d_bytes_per_step": th.nbytes, "d2h_bytes_per_step": 3 * 8 * len(th),
-                              "api": "qmps_energy_theta_host (rank 0's shard, pageable numpy buffers)", "n_gpus": 1}
+                              "api": "qmps_energy_theta_host (rank 0's shard; theta in pinned host memory, energies into a numpy array)", "n_gpus": 1}
             return res
         leg("cfg4", cfg4)
         if world > 1:
