@@ -372,7 +372,7 @@ def test_tdvp_tangent_large_D_on_tensor_cores_vs_oracle(env):
     for k in range(N):
         Ah = A[k].conj().transpose(0, 2, 1)
         op = LinearOperator((D * D, D * D), dtype=complex, matvec=lambda v: np.sum(A[k] @ v.reshape(D, D) @ Ah, axis=0).reshape(-1))
-        w, v = sp_eigs(op, k=1, which="LM", tol=1e-13)
+        w, v = sp_eigs(op, k=1, which="LM", tol=1e-13, v0=np.eye(D).reshape(-1).astype(complex), maxiter=20000)
         r = v[:, 0].reshape(D, D)
         r = r / np.trace(r)
         r = 0.5 * (r + r.conj().T)

@@ -621,7 +621,7 @@ def test_overlap_power_large_D_vs_sparse_eigensolver(env, D):
         Bh = Bt[k].conj().transpose(0, 2, 1)
         op = LinearOperator((D * D, D * D), dtype=complex,
                             matvec=lambda v: np.sum(A[k] @ v.reshape(D, D) @ Bh, axis=0).reshape(-1))
-        ref = eigs(op, k=1, which="LM", tol=1e-13)[0][0]
+        ref = eigs(op, k=1, which="LM", tol=1e-13, v0=np.eye(D).reshape(-1).astype(complex), maxiter=20000)[0][0]
         assert abs(eta[k] - ref) < 1e-8 * abs(ref)
         rk = res.r[k].cpu().numpy()
         assert np.abs(np.sum(A[k] @ rk @ Bh, axis=0) - eta[k] * rk).max() < 1e-6       # eigen-equation residual
