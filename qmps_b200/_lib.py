@@ -43,6 +43,7 @@ SIGNATURES = {
     "qmps_env_exact": ([_i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_env_exact_host": ([_i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i], _i),
     "qmps_get_env_exact_host": ([_i, _i64, _vp, _vp, _vp, _i, _i], _i),
+    "qmps_tm_apply": ([_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_scars_cost": ([_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "qmps_scars_trajectory": ([_vp, _vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint64, _i, _vp, _vp, _i, _vp], _i),
     "qmps_env_exact_packed": ([_i64, _vp, _i, _vp, _vp], _i),

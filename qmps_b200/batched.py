@@ -548,6 +548,18 @@ def tm_power(A, B, K, r0=None):
 
 
 
+def tm_apply(A, B, X):
+    """One unnormalised application of the (mixed) transfer map, Y[N, D, D] = sum_s A_s X B_s^dagger (``qmps_tm_apply``)."""
+    A = _cdev(A, A.dtype if isinstance(A, torch.Tensor) and A.dtype in _CDT else torch.complex128)
+    B = _cdev(B, A.dtype, A.device)
+    X = _cdev(X, A.dtype, A.device)
+    N, d, D, _ = A.shape
+    Y = torch.empty_like(X)
+    with torch.cuda.device(A.device):
+        L.check(L.load().qmps_tm_apply(d, D, N, _p(A), _p(B), _p(X), _p(Y), _dt(A), _stream()), "tm_apply")
+    return Y
+
+
 LoschmidtTrajectory = namedtuple("LoschmidtTrajectory", "theta step_cost echo")
 
 
@@ -645,8 +657,7 @@ def tdvp_tangent_large(AL, h, imaginary=False, tol=1e-11, chunk=32, max_iter=409
     AH = H_(AL)                                                              # A_s^dagger
     K, it_k = Bm.clone(), 0
     while it_k < max_iter:
-        KA = mm(K[:, None].expand(N, d, D, D), AL)                           # K A_s
-        Kn = Bm + mm(AH, KA).sum(dim=1)
+        Kn = Bm + tm_apply(AH, AH, K)                                        # sum_s A_s^dagger K A_s: one C-ABI call
         it_k += 1
         delta = (Kn - K).abs().amax(dim=(1, 2))
         K = Kn

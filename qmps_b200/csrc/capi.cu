@@ -103,6 +103,45 @@ int tm_power_f64(int d, int D, int64_t N, const void* A, const void* B, void* r_
   return 0;
 }
 
+// One UNNORMALISED application Y = sum_s A_s X B_s^dagger (the transfer-matrix apply itself: the building block of the
+// Neumann / Krylov iterations of the large-D tangent vector).  complex128: the two DMMA launches of tm_power_f64;
+// complex64: the SIMT tile kernel.
+int tm_apply_f64(int d, int D, int64_t N, const void* A, const void* B, const void* X, void* Y, cudaStream_t st) {
+  if (N == 0) return 0;
+  typedef cx<double> Z;
+  const size_t DD = (size_t)D * D;
+  const int tx = (D + ZG_TN - 1) / ZG_TN, ty = (D + ZG_TM - 1) / ZG_TM;
+  Scratch scratch(st);
+  Z* Tb = nullptr;
+  CK(scratch.get(&Tb, sizeof(Z) * N * d * DD));
+  if (int rc = allow_smem(zgemm_dmma_kernel<0>, ZG_SMEM_BYTES)) return rc;
+  if (int rc = allow_smem(zgemm_dmma_kernel<1>, ZG_SMEM_BYTES)) return rc;
+  const dim3 grid1(tx, ty, (unsigned)(N * d)), grid2(tx, ty, (unsigned)N);
+  ZgParams p1;
+  p1.M = D; p1.N = D; p1.K = D; p1.nsum = 1; p1.A = (const Z*)A; p1.B = (const Z*)X; p1.b_div = d; p1.C = Tb;
+  p1.norm_in = nullptr; p1.n_in = 0; p1.norm_out = nullptr;
+  zgemm_dmma_kernel<0><<<grid1, 256, ZG_SMEM_BYTES, st>>>(p1);
+  ZgParams p2;
+  p2.M = D; p2.N = D; p2.K = D; p2.nsum = d; p2.A = Tb; p2.B = (const Z*)B; p2.b_div = 1; p2.C = (Z*)Y;
+  p2.norm_in = nullptr; p2.n_in = 0; p2.norm_out = nullptr;
+  zgemm_dmma_kernel<1><<<grid2, 256, ZG_SMEM_BYTES, st>>>(p2);
+  CK(cudaGetLastError());
+  return 0;
+}
+int tm_apply_f32(int d, int D, int64_t N, const void* A, const void* B, const void* X, void* Y, cudaStream_t st) {
+  if (N == 0) return 0;
+  typedef float T;
+  const size_t DD = (size_t)D * D;
+  Scratch scratch(st);
+  cx<T>* Tb = nullptr;
+  CK(scratch.get(&Tb, sizeof(cx<T>) * N * d * DD));
+  const dim3 grid1((D + 31) / 32, (D + 31) / 32, (unsigned)(N * d)), grid2((D + 31) / 32, (D + 31) / 32, (unsigned)N);
+  zgemm_tile_kernel<T><<<grid1, 256, 0, st>>>(D, D, D, 1, (const cx<T>*)A, (const cx<T>*)X, 0, d, Tb, nullptr);
+  zgemm_tile_kernel<T><<<grid2, 256, 0, st>>>(D, D, D, d, Tb, (const cx<T>*)B, 1, 1, (cx<T>*)Y, nullptr);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 // ================================ exported C ABI =============================================
@@ -342,6 +381,26 @@ int qmps_rotosolve_fit(int64_t N, int nshift, const double* cost, double* theta_
   const int grid = (int)((N + 127) / 128 < (int64_t)sm_count() * 8 ? (N + 127) / 128 : (int64_t)sm_count() * 8);
   rotosolve_fit_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(N, nshift, cost, theta_star, fit, theta_io, P, coord);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int qmps_tm_apply(int d, int D, int64_t N, const void* A, const void* B, const void* X, void* Y, int dtype, void* stream) {
+  if (d < 1 || D < 1 || N < 0 || (N && (!A || !B || !X || !Y))) return fail(QMPS_ERR_ARG, "tm_apply: bad arguments");
+  if (dtype != QMPS_C128 && dtype != QMPS_C64) return fail(QMPS_ERR_ARG, "tm_apply: bad dtype");
+  if (X == Y) return fail(QMPS_ERR_ARG, "tm_apply: X and Y must not alias");
+  const int64_t chunk = 65535 / d;
+  if (chunk < 1) return fail(QMPS_ERR_UNSUPPORTED, "tm_apply: d > 65535");
+  const size_t csz = dtype == QMPS_C128 ? 16 : 8, DD = (size_t)D * D;
+  for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+    const int64_t n = (N - n0 < chunk) ? N - n0 : chunk;
+    const char* a = (const char*)A + csz * (size_t)n0 * d * DD;
+    const char* b = (const char*)B + csz * (size_t)n0 * d * DD;
+    const char* x = (const char*)X + csz * (size_t)n0 * DD;
+    char* y = (char*)Y + csz * (size_t)n0 * DD;
+    const int rc = dtype == QMPS_C128 ? tm_apply_f64(d, D, n, a, b, x, y, (cudaStream_t)stream)
+                                      : tm_apply_f32(d, D, n, a, b, x, y, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

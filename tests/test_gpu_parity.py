@@ -630,6 +630,20 @@ def test_overlap_power_large_D_vs_sparse_eigensolver(env, D):
     assert np.abs(res.rate.cpu().numpy() + np.log(np.abs(eta) ** 2)).max() < 1e-12
 
 
+@pytest.mark.parametrize("D,dt_name", [(8, "complex128"), (64, "complex128"), (100, "complex128"), (64, "complex64")])
+def test_tm_apply_vs_numpy(env, D, dt_name):
+    """qmps_tm_apply: one unnormalised application Y = sum_s A_s X B_s^dagger (general X, not Hermitian)."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    rng = np.random.default_rng(3 * D)
+    A, Bt = tensors(D, 3, 4400 + D, O), tensors(D, 3, 4500 + D, O)
+    X = rng.normal(size=(3, D, D)) + 1j * rng.normal(size=(3, D, D))
+    cdt = getattr(t, dt_name)
+    Y = B.tm_apply(t.from_numpy(A).cuda().to(cdt), t.from_numpy(Bt).cuda().to(cdt), t.from_numpy(X).cuda().to(cdt)).cpu().numpy()
+    ref = np.einsum("nsij,njk,nslk->nil", A, X, Bt.conj())
+    tol = 1e-12 if dt_name == "complex128" else 2e-5
+    assert np.abs(Y - ref).max() < tol * np.abs(ref).max()
+
+
 def test_tm_power_same_tensor_converges_to_environment(env):
     """Size-independent property: for A = B left-canonical the power method converges to the
     exact environment of the direct solver (trace-normalised), Rayleigh quotient -> 1."""

@@ -429,6 +429,7 @@ def test_c_abi_argument_validation_without_a_device(built):
         (lib.qmps_get_env_exact_host(3, 1, 1, 1, None, L.C128, 0), ERR_UNSUPPORTED, "unsupported D"),
         (lib.qmps_get_env_exact_host(2, 1, None, None, None, L.C128, 0), ERR_ARG, "get_env_exact_host"),
         (lib.qmps_zgemm_c128_i8(1, 64, 32, 64, None, None, 0, None, None), ERR_ARG, "zgemm_c128_i8"),
+        (lib.qmps_tm_apply(2, 4, 1, 1, 1, 8, 8, L.C128, None), ERR_ARG, "must not alias"),
     ]
     for rc, want, msg in cases:
         assert rc == want, (rc, want, msg)
