@@ -430,6 +430,7 @@ def run_ours(args):
             leg("cfg1_scalar", lambda: BL.leg_scalar_latency(torch, dev))
             leg("cfg7", lambda: BL.leg_loschmidt(torch, B, R, dev, 2, peaks, scale=args.sub_scale))
             leg("cfg3", lambda: BL.leg_loschmidt(torch, B, R, dev, 4, peaks, scale=args.sub_scale))
+            leg("loschmidt_d8", lambda: BL.leg_loschmidt(torch, B, R, dev, 8, peaks, scale=args.sub_scale, c64_too=False))
             leg("f3_tdvp_large", lambda: BL.leg_tdvp_large(torch, B, dev, peaks))
             for D in (64, 256):
                 for tag in ("c128", "c64"):
@@ -477,12 +478,12 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"4 x {pc} per-call solves per core on {cores} cores (oracle port of qmps/tools.py:176-182: "
                                               f"unitary_to_tensor, dense eig, cholesky, V[:,0] -- the outputs the GPU arm writes)"}
-            kinds = ["env_d2", "loschmidt_d2", "loschmidt_d4", "energy_d8", "power_d64", "power_d256"]
+            kinds = ["env_d2", "loschmidt_d2", "loschmidt_d4", "loschmidt_d8", "energy_d8", "power_d64", "power_d256"]
             try:
                 cb, cores2 = BL.cpu_baselines(kinds, seconds=args.cpu_seconds)
                 line["cpu_baseline"]["vectorised_value"] = cb["env_d2"]["vectorised"]
                 line["cpu_baseline"]["vectorised_note"] = "BASELINE.md B2: the same algorithm as stacked numpy.linalg calls (oracle/stacked.py), one process per core"
-                key = {7: "loschmidt_d2", 3: "loschmidt_d4", 4: "energy_d8"}
+                key = {7: "loschmidt_d2", 3: "loschmidt_d4", 38: "loschmidt_d8", 4: "energy_d8"}
                 for sres in subs:
                     k = key.get(sres["cfg"])
                     if sres["cfg"] == 5:

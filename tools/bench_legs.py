@@ -99,11 +99,11 @@ def _port_worker(args):
     if kind == "env_d2":
         Us = [unitary_group.rvs(4, random_state=seed * 131 + k) for k in range(64)]
         fn = lambda k: O.env_exact_parts(O.unitary_to_tensor(Us[k & 63]))          # (eta, r, C, V[:,0])
-    elif kind in ("loschmidt_d2", "loschmidt_d4"):
-        D = 2 if kind.endswith("d2") else 4
+    elif kind in ("loschmidt_d2", "loschmidt_d4", "loschmidt_d8"):
+        D = int(kind[-1])
         tens = (lambda p: O.unitary_to_tensor(O.shallow_full_state_tensor(p))) if D == 2 else \
-               (lambda p: O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(4, p)))
-        P = 15 if D == 2 else 12
+               (lambda p: O.unitary_to_tensor(O.shallow_cnot_state_tensor_nonuniform(D, p)))
+        P = {2: 15, 4: 12, 8: 24}[D]
         A0 = tens(rng.normal(size=P))
         W = tfim_gates(2)[1]
         thetas = rng.normal(size=(16, P))
@@ -225,10 +225,14 @@ def _roof(bound, achieved, peak, unit, kernel, per_unit, note=None, traffic=None
 
 
 def leg_loschmidt(torch, B, R, dev, D, peaks, scale=1.0, c64_too=True):
-    """cfg 7 (D = 2) / cfg 3 (D = 4): 4096 parameter sets x 1000 times, one qmps_loschmidt_batched call."""
+    """cfg 7 (D = 2) / cfg 3 (D = 4): 4096 parameter sets x 1000 times, one qmps_loschmidt_batched call; D = 8 (the metric's
+    middle bond dimension; 64 x 64 mixed maps on the generic group kernel): 256 parameter sets x 100 times."""
     NP, NT = max(64, int(4096 * scale)), 1000
     if D == 2:
         P, seed, gate = 15, 7, R.ShallowFullStateTensor(2, np.zeros(15))
+    elif D == 8:
+        NP, NT = max(32, int(256 * scale)), 100
+        P, seed, gate = 24, 8, R.ShallowCNOTStateTensor_nonuniform(8, np.zeros(24))
     else:
         P, seed, gate = 12, 2, R.ShallowCNOTStateTensor_nonuniform(4, np.zeros(12))
     prog = gate.program()
@@ -236,18 +240,18 @@ def leg_loschmidt(torch, B, R, dev, D, peaks, scale=1.0, c64_too=True):
     theta = torch.from_numpy(theta_h).to(dev)
     A0 = B.ansatz_tensors(prog, theta[:1])[0]
     A0_h = A0.cpu().numpy()
-    W_h = tfim_gates(NT)
+    W_h = tfim_gates(1000)[:NT].copy()
     W = torch.from_numpy(W_h).to(dev)
     ms = timed_ms(torch, lambda: B.loschmidt_costs(prog, theta, A0, W), reps=3, warm=1)
     units = NP * NT
     n = D * D
     flops = 100.0 * n ** 3
-    res = {"cfg": 7 if D == 2 else 3, "workload": f"loschmidt_D{D}_{NP}x{NT}_c128",
+    res = {"cfg": {2: 7, 4: 3, 8: 38}[D], "workload": f"loschmidt_D{D}_{NP}x{NT}_c128",
            "metric": "loschmidt_echo_steps_per_sec", "unit": "steps/s", "dtype": "c128",
            "value": units / ms * 1e3, "ms_per_step": ms, "units_per_step": units,
            "api": "qmps_loschmidt_batched (ansatz, merge, gate-merge, fixed points; 4 launches)",
            "roofline": _roof("fp64", units * flops / ms * 1e3 / 1e12, peaks["fp64_fma_tflops"], "TFLOP/s",
-                             "fp_d2_kernel<double>" if D == 2 else "fp16s8_kernel<double>", f"{flops:.3g} real flops (100 n^3, n = {n})",
+                             {2: "fp_d2_kernel<double>", 4: "fp16s8_kernel<double>", 8: "fixed_point_kernel<double,128>"}[D], f"{flops:.3g} real flops (100 n^3, n = {n})",
                              note="eigenvalues of every map by Hessenberg + shifted QR; iteration counts are data dependent, "
                                   "the algorithmic count is the LAPACK-style estimate")}
     if c64_too:
