@@ -373,8 +373,9 @@ def loschmidt_costs_host(program, theta, A0, W, dtype=np.complex128, device=0, w
     return (cost, echo) if want_echo else cost
 
 
-def energy_theta_host(program, theta, H, coord=None, shifts=None, dtype=np.complex128, device=0):
-    """``energy_theta`` on HOST arrays through ``qmps_energy_theta_host``: 8 P bytes in, 8 bytes per shift out."""
+def energy_theta_host(program, theta, H, coord=None, shifts=None, dtype=np.complex128, device=0, want_status=False):
+    """``energy_theta`` on HOST arrays through ``qmps_energy_theta_host``: 8 P bytes in, 8 bytes per shift out, one
+    synchronisation (this is also the scalar path of the optimiser classes: one parameter vector per call)."""
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     Hh = np.ascontiguousarray(H, dtype=dtype)
     N, P = theta.shape
@@ -382,12 +383,13 @@ def energy_theta_host(program, theta, H, coord=None, shifts=None, dtype=np.compl
     sh = np.ascontiguousarray(shifts, dtype=np.float64) if ns else None
     rd = np.float64 if np.dtype(dtype) == np.complex128 else np.float32
     e = np.empty((N, ns) if ns else (N,), dtype=rd)
+    st = np.zeros((N, ns) if ns else (N,), dtype=np.int32) if want_status else None
     ops = program.c_ops()
     L.check(L.require_device().qmps_energy_theta_host(
         ops, len(program), program.nq, N, P, theta.ctypes.data, Hh.ctypes.data, -1 if coord is None else int(coord),
-        sh.ctypes.data if ns else None, ns, e.ctypes.data, None, L.C128 if np.dtype(dtype) == np.complex128 else L.C64,
-        int(device)), "energy_theta_host")
-    return e
+        sh.ctypes.data if ns else None, ns, e.ctypes.data, st.ctypes.data if want_status else None,
+        L.C128 if np.dtype(dtype) == np.complex128 else L.C64, int(device)), "energy_theta_host")
+    return (e, st) if want_status else e
 
 
 def overlap_theta(program, theta1, theta2, dtype=torch.complex128):

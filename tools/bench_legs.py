@@ -380,10 +380,30 @@ def leg_scalar_latency(torch, dev):
         O.get_env_exact(U)
     cpu_us = (time.perf_counter() - t0) / len(Us) * 1e6
     err = max(float(np.abs(np.abs(T.get_env_exact(U)[:, 0]) - np.abs(O.get_env_exact(U)[:, 0])).max()) for U in Us[:8])
+    # the scalar cost function the reference's optimisers call (ground_state.py:150-168): one parameter vector per call
+    from qmps_b200.ground_state import SparseFullEnergyOptimizer
+    Hm = O.tfim_matrix(1.0)
+    opt = SparseFullEnergyOptimizer(Hm, D=2, depth=2)
+    ths = np.random.default_rng(5).normal(size=(64, len(opt.initial_guess)))
+    for th in ths[:8]:
+        opt.objective_function(th)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        for th in ths:
+            opt.objective_function(th)
+    obj_us = (time.perf_counter() - t0) / (4 * len(ths)) * 1e6
+    ref_fn = lambda th: O.energy_transfer(O.unitary_to_tensor(O.shallow_cnot_state_tensor(2, th)), Hm)   # noqa: E731
+    t0 = time.perf_counter()
+    for th in ths:
+        ref_fn(th)
+    obj_cpu_us = (time.perf_counter() - t0) / len(ths) * 1e6
+    obj_err = max(abs(opt.objective_function(th) - ref_fn(th)) for th in ths[:8])
     return {"cfg": 1, "workload": "get_env_exact_batch_of_one_D2_c128 (scalar drop-in latency)", "metric": "latency_per_call", "unit": "us",
             "dtype": "c128", "value": gpu_us, "higher_is_better": False, "api": "qmps_b200.tools.get_env_exact -> qmps_get_env_exact_host (H2D, 3 kernels, D2H, 1 sync)",
             "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port", "sample": "64 per-call oracle.get_env_exact (qmps/tools.py:176-182 restated)"},
             "max_abs_diff_first_column_moduli": err,
+            "objective_function": {"value": obj_us, "unit": "us", "cpu_port_us": obj_cpu_us, "max_abs_diff": obj_err,
+                                   "api": "SparseFullEnergyOptimizer.objective_function -> qmps_energy_theta_host (one call, one sync)"},
             "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "kernel": "env_d2_stream_kernel + env2u_kernel",
                          "note": "three launches + two PCIe copies + one synchronisation; nothing here is throughput-bound"}}
 
