@@ -199,8 +199,9 @@ int qmps_loschmidt_rate(int64_t NT, const double* t, double g0, double g1, doubl
 /* cfg 5  classical power method (qmps.ipynb cells 29-32): K normalised applications
  *     r <- sum_s A_s r B_s^dagger / |.|_F.  A, B [N][d][D][D]; r_io [N][D][D] (start
  *     vector in, r_K out); rayleigh [N] complex = <r_K, E r_K> (optional). */
-/* one UNNORMALISED application of the (mixed) transfer map, Y [N][D][D] = sum_s A_s X B_s^dagger (X != Y): the building
- *     block of the Neumann / Krylov iterations a large-D caller runs (the tangent vector's left-Hamiltonian solve). */
+/* one UNNORMALISED application of the (mixed) transfer map, Y [N][D][D] = sum_s A_s X B_s^dagger (X != Y): the body of
+ *     the power-method loop of qmps.ipynb cells 29-32 without its normalisation, and the building block of the Neumann /
+ *     Krylov iterations a large-D caller runs (iMPS.dA_dt at D > 16: scripts/classical_time_evolution.py:22-26). */
 int qmps_tm_apply(int d, int D, int64_t N, const void* A, const void* B, const void* X, void* Y, int dtype, void* stream);
 int qmps_tm_power(int d, int D, int64_t N, const void* A, const void* B, void* r_io, int K,
                   void* rayleigh, int dtype, void* stream);
