@@ -478,7 +478,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"4 x {pc} per-call solves per core on {cores} cores (oracle port of qmps/tools.py:176-182: "
                                               f"unitary_to_tensor, dense eig, cholesky, V[:,0] -- the outputs the GPU arm writes)"}
-            kinds = ["env_d2", "loschmidt_d2", "loschmidt_d4", "loschmidt_d8", "energy_d8", "power_d64", "power_d256"]
+            kinds = ["env_d2", "loschmidt_d2", "loschmidt_d4", "loschmidt_d8", "energy_d8", "power_d64", "power_d256", "tdvp_d64"]
             try:
                 cb, cores2 = BL.cpu_baselines(kinds, seconds=args.cpu_seconds)
                 line["cpu_baseline"]["vectorised_value"] = cb["env_d2"]["vectorised"]
@@ -488,12 +488,17 @@ def run_ours(args):
                     k = key.get(sres["cfg"])
                     if sres["cfg"] == 5:
                         k = "power_d64" if "_D64_" in sres["workload"] else "power_d256"
+                        if sres["workload"].startswith("tdvp_tangent"):
+                            k = "tdvp_d64"
                     if sres["cfg"] == 2:
                         k = "env_d2"
                     if k:
                         sres["cpu_baseline"] = {"value": cb[k]["port"], "vectorised_value": cb[k]["vectorised"], "unit": sres["unit"], "cores": cores2,
                                                 "kind": "port", "sample": f"{args.cpu_seconds:.0f} s of per-call oracle evaluations per core (port); "
                                                                           f"{args.cpu_seconds:.0f} s of stacked / threaded numpy (vectorised)"}
+                        if k == "tdvp_d64":
+                            sres["cpu_baseline"]["sample"] = (f"{args.cpu_seconds:.0f} s of the same iterative algorithm (power method + Neumann series) in numpy on the "
+                                                              "threaded BLAS of all cores, one tensor at a time (tools/bench_legs.py cpu_tdvp_threaded)")
             except Exception as e:  # noqa: BLE001
                 line["sub_errors"] = line.get("sub_errors", []) + [f"cpu_baselines: {type(e).__name__}: {e}"[:300]]
         emit(line)

@@ -23,7 +23,7 @@ inline int fail(int code, const std::string& msg) { last_error() = msg; return c
   } while (0)
 
 // tuning knobs (qmps_set_option); defaults are the measured best
-enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_TC_POWER = 4, OPT_TC_PERSISTENT = 5, OPT_FP_GROUP = 6, OPT_FP_BLOCK = 7, OPT_ER_WIDE = 8, OPT_FP_D2 = 9, OPT_BW_THREAD = 10, OPT_I8_POWER = 11, OPT_TC_PRESPLIT = 12, OPT_COUNT = 13 };
+enum { OPT_D2_PDL = 0, OPT_D2_CTAS_PER_SM = 1, OPT_FP16_FAST = 2, OPT_ENV_REAL = 3, OPT_TC_POWER = 4, OPT_TC_PERSISTENT = 5, OPT_FP_GROUP = 6, OPT_FP_BLOCK = 7, OPT_ER_WIDE = 8, OPT_FP_D2 = 9, OPT_BW_THREAD = 10, OPT_I8_POWER = 11, OPT_TC_PRESPLIT = 12, OPT_FP64_FAST = 13, OPT_COUNT = 14 };
 int option_get(int key);                          // defined in capi.cu
 
 inline int sm_count() {

@@ -4,6 +4,7 @@
 #include "launch_envreal.cuh"
 #include "kernels_fp16x8.cuh"
 #include "kernels_fp16s.cuh"
+#include "kernels_fp64w.cuh"
 #include "kernels_fpd2.cuh"
 
 using namespace qmps;
@@ -118,6 +119,20 @@ int launch_fp16(const FpParams& p, cudaStream_t st) {
   }
 }
 
+// D = 8 eigenvalue-only path (kernels_fp64w.cuh): one warp per 64 x 64 map, matrix in a skewed shared tile
+int launch_fp64w(FpParams p, cudaStream_t st) {
+  const Fp64wLayout<REAL> L = fp64w_layout<REAL>();
+  const size_t smem = L.total;
+  auto kern = fp64w_kernel<REAL>;
+  if (int rc = allow_smem(kern, smem)) return rc;
+  int grid = 1;
+  if (int rc = persistent_grid(kern, 32, smem, p.N, &grid)) return rc;
+  p.ws = nullptr; p.ws_stride = 0;
+  kern<<<grid, 32, smem, st>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // D = 2 eigenvalue-only path (kernels_fpd2.cuh): one thread per problem, registers only
 template <bool VEC> int launch_fp_d2_v(FpParams p, cudaStream_t st) {
   auto kern = fp_d2_kernel<REAL, VEC>;
@@ -180,6 +195,7 @@ int env_generic_f32(const EnvParams& p, int mode, cudaStream_t st) {
 int fixed_point_f32(const FpParams& p, cudaStream_t st) {
   if (p.D == 2 && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
+  if (p.D == 8 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP64_FAST)) return launch_fp64w(p, st);
   // complex64, n = 16: 8 lanes per problem measured 24 % faster than 16 (profiles/sweep_fp_r01e.jsonl)
   if (p.D == 4 && (option_get(OPT_FP_GROUP) == 8 || option_get(OPT_FP_GROUP) == 0)) return launch_fp<8>(p, st);
   if (p.D == 4 && option_get(OPT_FP_GROUP) == 4) return launch_fp<4>(p, st);

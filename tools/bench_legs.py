@@ -193,6 +193,54 @@ def cpu_power_threaded(D, N, seconds):
     return n / (time.perf_counter() - t0)
 
 
+def cpu_tdvp_threaded(D, seconds, tol=1e-11):
+    """CPU arm of the large-D TDVP tangent leg: the SAME iterative algorithm as batched.tdvp_tangent_large (power method
+    for r, Neumann series of the left transfer map for K, the formulas of oracle/tdvp.py:59-83) in numpy on the threaded
+    BLAS of the box (all cores, one tensor at a time) -- the dense D^2 x D^2 solve of the oracle takes ~10 s per tangent at
+    D = 64 and is not what a CPU user would run.  Returns tangents/s."""
+    rng = np.random.default_rng(64)
+    d = 2
+    Q = np.linalg.qr(rng.normal(size=(d * D, D)) + 1j * rng.normal(size=(d * D, D)))[0]
+    AL = np.ascontiguousarray(Q.reshape(D, d, D).transpose(1, 0, 2))
+    h = (-np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0])) + 0.35 * (np.kron([[0, 1], [1, 0]], np.eye(2)) + np.kron(np.eye(2), [[0, 1], [1, 0]]))).reshape(d, d, d, d).astype(complex)
+    AH = np.ascontiguousarray(AL.conj().transpose(0, 2, 1))
+
+    def one():
+        r, prev = np.eye(D, dtype=complex) / D, None
+        for it in range(4096):
+            x = sum(AL[s] @ r @ AH[s] for s in range(d))
+            ray = np.vdot(r, x).real / np.vdot(r, r).real
+            r = x / np.linalg.norm(x)
+            if it % 32 == 31:
+                if prev is not None and abs(ray - prev) <= tol:
+                    break
+                prev = ray
+        r = 0.5 * (r + r.conj().T); r = r / np.trace(r).real
+        AA = np.einsum("sij,tjk->stik", AL, AL)
+        C = np.einsum("abcd,cdik->abik", h, AA)
+        Hl = np.einsum("stji,stjk->ik", AA.conj(), C)
+        e = np.einsum("ik,ki->", Hl, r).real
+        Bm = Hl - e * np.eye(D)
+        K = Bm.copy()
+        for _ in range(4096):
+            Kn = Bm + sum(AH[s] @ K @ AL[s] for s in range(d))
+            done = np.abs(Kn - K).max() <= tol * np.abs(Kn).max()
+            K = Kn
+            if done:
+                break
+        K = K - np.einsum("ik,ki->", K, r) * np.eye(D)
+        rinv = np.linalg.inv(r)
+        G = (np.einsum("stik,kl,tml,mj->sij", C, r, AL.conj(), rinv, optimize=True) + np.einsum("tki,tskj->sij", AL.conj(), C, optimize=True)
+             + np.einsum("ik,skj->sij", K, AL))
+        P = np.einsum("ski,skj->ij", AL.conj(), G)
+        return -1j * (G - np.einsum("sik,kj->sij", AL, P))
+    one()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        one(); n += 1
+    return n / (time.perf_counter() - t0)
+
+
 def cpu_baselines(kinds, seconds=2.0, cores=None):
     """{kind: {"port": rate, "vectorised": rate or None}} on `cores` host cores."""
     import multiprocessing as mp
@@ -201,6 +249,8 @@ def cpu_baselines(kinds, seconds=2.0, cores=None):
     with mp.get_context("fork").Pool(cores) as pool:
         pool.map(_port_worker, [("env_d2", 0.2, c) for c in range(cores)])      # imports, page-in
         for kind in kinds:
+            if kind == "tdvp_d64":
+                continue
             port = cpu_rate(pool, cores, kind, seconds)
             vec = None
             if kind in ("env_d2", "loschmidt_d2", "loschmidt_d4", "energy_d8"):
@@ -210,6 +260,8 @@ def cpu_baselines(kinds, seconds=2.0, cores=None):
         if kind in ("power_d64", "power_d256"):
             D = 64 if kind.endswith("64") else 256
             out[kind]["vectorised"] = cpu_power_threaded(D, 64 if D == 64 else 8, seconds)
+    if "tdvp_d64" in kinds:
+        out["tdvp_d64"] = {"port": cpu_tdvp_threaded(64, seconds), "vectorised": None}
     return out, cores
 
 
