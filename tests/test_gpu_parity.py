@@ -363,6 +363,77 @@ def test_fixed_point_d4_degenerate_inputs(env):
         assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
 
 
+@pytest.mark.parametrize("left", [False, True])
+@pytest.mark.parametrize("d", [2, 4])
+def test_fixed_point_d8_warp_kernel(env, left, d):
+    """The warp-per-problem D = 8 kernel (kernels_fp64w.cuh, eigenvalue only, the default) against numpy's dense eig
+    of the oracle's transfer matrix and against the generic CTA-per-problem kernel on the same inputs; d = 4 is the
+    two-site (merged) map of the Loschmidt cost.  37 problems: fewer than the persistent grid, an odd count."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    count = 37
+    A, Bt = tensors(8, count, 2300 + d, O), tensors(8, count, 2900 + d, O)
+    if d == 4:
+        A = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", A, A[::-1]).reshape(count, 4, 8, 8))
+        Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt[::-1]).reshape(count, 4, 8, 8))
+    Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
+    lib = L.load()
+    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+    f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
+    lib.qmps_set_option(b"fp64_fast", 0)
+    try:
+        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+    finally:
+        lib.qmps_set_option(b"fp64_fast", 1)
+    assert int(fast.status.abs().sum()) == 0
+    assert (fast.eta - slow.eta).abs().max().item() < 1e-12
+    for k in range(count):
+        E = sum(np.kron(A[k, s], Bt[k, s].conj()) for s in range(d))
+        w = np.linalg.eigvals(E)
+        x0 = np.abs(w).max()
+        assert abs(abs(fast.eta[k].item()) - x0) < TOL
+        assert abs(fast.cost[k].item() + np.sqrt(x0)) < TOL
+        assert abs(fast.fid[k].item() - x0 ** 2) < TOL
+        assert abs(fast.echo[k].item() + np.log(x0 ** 2)) < TOL * 10
+        lam = np.conj(fast.eta[k].item()) if left else fast.eta[k].item()
+        assert np.abs(w - lam).min() < 1e-11                   # it IS an eigenvalue of E, not just the right modulus
+    assert (f32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5          # complex64 mode
+    # outer pairing (the Loschmidt grid: one reference tensor against many) goes through the same kernel
+    outer = B.fixed_point(Ad[:2], Bd[:5], pair="outer", left=left, want_vec=False)
+    for i in range(2):
+        for j in range(5):
+            E = sum(np.kron(A[i, s], Bt[j, s].conj()) for s in range(d))
+            assert abs(abs(outer.eta[i, j].item()) - np.abs(np.linalg.eigvals(E)).max()) < TOL
+
+
+def test_fixed_point_d8_degenerate_inputs(env):
+    """Edge cases of the D = 8 QR kernel: identical tensors (|eta| = 1), a product state (rank-one map: 63 zero
+    eigenvalues, every sub-diagonal entry deflates at once), the zero tensor, and a block-diagonal pair whose 64 x 64 map
+    splits in the middle of the matrix (windows that start above row 32)."""
+    t, B, O = env["torch"], env["B"], env["O"]
+    A = tensors(8, 3, 15, O)
+    prod = np.zeros((1, 2, 8, 8), complex); prod[0, 0, 0, 0] = 1.0
+    zero = np.zeros((1, 2, 8, 8), complex)
+    blk = np.zeros((1, 2, 8, 8), complex)
+    A4 = tensors(4, 2, 16, O)
+    blk[0, :, :4, :4] = A4[0]; blk[0, :, 4:, 4:] = 0.5 * A4[1]
+    X = t.from_numpy(np.concatenate([A, prod, zero, blk])).cuda()
+    lib = env["L"].load()
+    res = {}
+    for fast in (0, 1):
+        lib.qmps_set_option(b"fp64_fast", fast)
+        try:
+            fp = B.fixed_point(X, X, want_vec=False)
+            res[fast] = fp.eta.cpu().numpy()
+            assert int(fp.status.abs().sum().item()) == 0
+        finally:
+            lib.qmps_set_option(b"fp64_fast", 1)
+        eta = res[fast]
+        assert np.abs(np.abs(eta[:3]) - 1).max() < 1e-12
+        assert abs(abs(eta[3]) - 1) < 1e-12 and abs(eta[4]) == 0
+        assert abs(abs(eta[5]) - 1) < 1e-12                    # the leading block is an isometry with itself
+    assert np.abs(np.abs(res[0]) - np.abs(res[1])).max() < 1e-12
+
+
 def test_fixed_point_outer_and_broadcast(env):
     t, B, O = env["torch"], env["B"], env["O"]
     A, Bt = tensors(2, 3, 1, O), tensors(2, 5, 2, O)
