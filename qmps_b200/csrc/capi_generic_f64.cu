@@ -5,6 +5,7 @@
 #include "kernels_fp16x8.cuh"
 #include "kernels_fp16s.cuh"
 #include "kernels_fp64w.cuh"
+#include "kernels_fp64p.cuh"
 #include "kernels_fpd2.cuh"
 
 using namespace qmps;
@@ -92,11 +93,11 @@ int launch_fp16s(FpParams p, cudaStream_t st) {
   CK(cudaGetLastError());
   return 0;
 }
-int launch_fp16s8(FpParams p, cudaStream_t st) {
+template <bool FASTRSQ> int launch_fp16s8(FpParams p, cudaStream_t st) {
   const Fp16sLayout<REAL> L = fp16s_layout<REAL>();
   const int block = 64, gpc = block / 8;
   const size_t smem = L.total * gpc;
-  auto kern = fp16s8_kernel<REAL>;
+  auto kern = fp16s8_kernel<REAL, FASTRSQ>;
   if (int rc = allow_smem(kern, smem)) return rc;
   int grid = 1;
   if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
@@ -114,7 +115,8 @@ int launch_fp16(const FpParams& p, cudaStream_t st) {
     case 4: return launch_fp16x8_v<5>(p, st);
     case 5: return launch_fp16x8_v<6>(p, st);
     case 6: return launch_fp16s(p, st);
-    case 7: return launch_fp16s8(p, st);
+    case 7: return launch_fp16s8<false>(p, st);
+    case 8: return launch_fp16s8<true>(p, st);      // + branch-free reciprocal square root in the sweep body
     default: return launch_fp16_v<3>(p, st);
   }
 }
@@ -130,6 +132,32 @@ int launch_fp64w(FpParams p, cudaStream_t st) {
   p.ws = nullptr; p.ws_stride = 0;
   kern<<<grid, 32, smem, st>>>(p);
   CK(cudaGetLastError());
+  return 0;
+}
+
+// packed two-kernel form (kernels_fp64p.cuh): Hessenberg reduction -> packed workspace -> QR with twice the warps per SM
+int launch_fp64p(FpParams p, cudaStream_t st) {
+  const int64_t CH = 16384;                                    // problems per launch pair: 34 KB (complex128) of workspace each
+  const int64_t nws = p.N < CH ? p.N : CH;
+  const size_t smem_h = fp64w_layout<REAL>().total, smem_q = fp64p_layout<REAL>().total;
+  auto kh = fp64p_hess_kernel<REAL>;
+  auto kq = fp64p_qr_kernel<REAL>;
+  if (int rc = allow_smem(kh, smem_h)) return rc;
+  if (int rc = allow_smem(kq, smem_q)) return rc;
+  void* ws = nullptr;
+  CK(malloc_async(&ws, sizeof(cx<REAL>) * (size_t)F64P_SIZE * nws, st));
+  p.ws = ws; p.ws_stride = F64P_SIZE;
+  for (int64_t off = 0; off < p.N; off += CH) {
+    p.pid_offset = off; p.n_chunk = p.N - off < CH ? p.N - off : CH;
+    int gh = 1, gq = 1;
+    if (int rc = persistent_grid(kh, 32, smem_h, p.n_chunk, &gh)) { cudaFreeAsync(ws, st); return rc; }
+    if (int rc = persistent_grid(kq, 32, smem_q, p.n_chunk, &gq)) { cudaFreeAsync(ws, st); return rc; }
+    kh<<<gh, 32, smem_h, st>>>(p);
+    kq<<<gq, 32, smem_q, st>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  CK(e);
   return 0;
 }
 
@@ -204,6 +232,7 @@ int fp16_debug_f64(unsigned long long* out, int reset) {
 int fixed_point_f64(const FpParams& p, cudaStream_t st) {
   if (p.D == 2 && p.d <= 16 && option_get(OPT_FP_D2)) return launch_fp_d2(p, st);
   if (p.D == 4 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP16_FAST)) return launch_fp16(p, st);
+  if (p.D == 8 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP64_FAST) == 2) return launch_fp64p(p, st);
   if (p.D == 8 && p.vec == nullptr && p.d <= 16 && option_get(OPT_FP64_FAST)) return launch_fp64w(p, st);
   if (p.D == 4 && option_get(OPT_FP_GROUP) == 8) return launch_fp<8>(p, st);
   if (p.D == 4 && option_get(OPT_FP_GROUP) == 4) return launch_fp<4>(p, st);

@@ -52,6 +52,19 @@ template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
 template <> __device__ __forceinline__ double rsqrt_t<double>(double x) { return rsqrt(x); }
 template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rsqrtf(x); }
 
+// branch-free 1/sqrt(x) for a normal positive x: MUFU.RSQ64H seed (2^-22.9) + two Newton steps.  CUDA's rsqrt() carries
+// a slow-path call whose branches split the sweep body into basic blocks the scheduler cannot interleave.
+template <typename T> __device__ __forceinline__ T rsq_fast(T x);
+template <> __device__ __forceinline__ double rsq_fast<double>(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+template <> __device__ __forceinline__ float rsq_fast<float>(float x) { return rsqrtf(x); }
+
 template <typename T> __device__ __forceinline__ cx<T> shfl16(cx<T> v, int src) {
   cx<T> r;
   r.re = __shfl_sync(0xffffffffu, v.re, src, 16);

@@ -261,7 +261,7 @@ fp16s_kernel(FpParams p) {
 // instructions of a step in the half-warp form, profiles/ncu_fp16_r02e.txt) is shared by four problems
 // instead of two, and structural zeros are skipped: columns 0..7 have nothing below row 8, rows 8..15
 // nothing left of column 7.
-template <typename T>
+template <typename T, bool FASTRSQ = false>
 __global__ void __launch_bounds__(64, 6)
 fp16s8_kernel(FpParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -447,7 +447,7 @@ fp16s8_kernel(FpParams p) {
           const cx<T> f = low ? pa : pb, g = low ? qa : qb;  // column i-1 is an "a" column iff i-1 < 8
           const T nr2 = norm2(f) + norm2(g);
           const bool ok = act && nr2 > T(0);
-          const T inr = rsqrt_t<T>(nr2);
+          const T inr = FASTRSQ ? rsq_fast<T>(nr2) : rsqrt_t<T>(nr2);   // FASTRSQ: no slow-path branch inside the sweep body
           cx<T> c = f * inr, s = g * inr;
           const T nr = nr2 * inr;
           const bool owner = q == ((i - 1) & 7);

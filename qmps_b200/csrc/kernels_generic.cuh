@@ -198,6 +198,7 @@ struct FpParams {
   void* eta; void* vec; void* cost; void* echo; void* fid; int32_t* status;
   void* ws; size_t ws_stride;
   int vec_gauge;                 // QMPS_GAUGE_TRACE (0) / QMPS_GAUGE_ZGEEV (1)
+  int64_t pid_offset, n_chunk;   // kernels_fp64p.cuh: the slice of the batch one launch pair works on (set by its launcher)
 };
 
 template <typename T, int G>

@@ -277,16 +277,16 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
     try:
         slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)  # generic shared-memory group kernel
     finally:
-        lib.qmps_set_option(b"fp16_fast", 7)
+        lib.qmps_set_option(b"fp16_fast", 8)
     assert (default.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
-    for variant in (1, 3, 6, 7):       # half-warp / quarter-warp register forms, shared-resident half / quarter warp
+    for variant in (1, 3, 6, 7, 8):    # half-warp / quarter-warp register forms, shared-resident half / quarter warp (8: branch-free rsqrt)
         lib.qmps_set_option(b"fp16_fast", variant)
         try:
             fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
             f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
             t.cuda.synchronize()
         finally:
-            lib.qmps_set_option(b"fp16_fast", 7)
+            lib.qmps_set_option(b"fp16_fast", 8)
         assert int(fast.status.abs().sum()) == 0
         assert (fast.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
         for k in range(count):
@@ -352,13 +352,13 @@ def test_fixed_point_d4_degenerate_inputs(env):
     zero = np.zeros((1, 2, 4, 4), complex)
     X = t.from_numpy(np.concatenate([A, prod, zero])).cuda()
     lib = env["L"].load()
-    for fast in (0, 1, 3, 6, 7):
+    for fast in (0, 1, 3, 6, 7, 8):
         lib.qmps_set_option(b"fp16_fast", fast)
         try:
             fp = B.fixed_point(X, X, want_vec=False)
             eta = fp.eta.cpu().numpy()
         finally:
-            lib.qmps_set_option(b"fp16_fast", 7)
+            lib.qmps_set_option(b"fp16_fast", 8)
         assert np.abs(np.abs(eta[:4]) - 1).max() < 1e-12
         assert abs(abs(eta[4]) - 1) < 1e-12 and abs(eta[5]) == 0
 
@@ -366,7 +366,7 @@ def test_fixed_point_d4_degenerate_inputs(env):
 @pytest.mark.parametrize("left", [False, True])
 @pytest.mark.parametrize("d", [2, 4])
 def test_fixed_point_d8_warp_kernel(env, left, d):
-    """The warp-per-problem D = 8 kernel (kernels_fp64w.cuh, eigenvalue only, the default) against numpy's dense eig
+    """The warp-per-problem D = 8 kernels (kernels_fp64p.cuh, the default, and kernels_fp64w.cuh) against numpy's dense eig
     of the oracle's transfer matrix and against the generic CTA-per-problem kernel on the same inputs; d = 4 is the
     two-site (merged) map of the Loschmidt cost.  37 problems: fewer than the persistent grid, an odd count."""
     t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
@@ -377,15 +377,20 @@ def test_fixed_point_d8_warp_kernel(env, left, d):
         Bt = np.ascontiguousarray(np.einsum("naik,nbkj->nabij", Bt, Bt[::-1]).reshape(count, 4, 8, 8))
     Ad, Bd = t.from_numpy(A).cuda(), t.from_numpy(Bt).cuda()
     lib = L.load()
-    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
+    fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)     # default: packed two-kernel form (kernels_fp64p.cuh)
     f32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
-    lib.qmps_set_option(b"fp64_fast", 0)
     try:
-        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)
-    finally:
+        lib.qmps_set_option(b"fp64_fast", 0)
+        slow = B.fixed_point(Ad, Bd, left=left, want_vec=False)  # generic CTA-per-problem kernel
         lib.qmps_set_option(b"fp64_fast", 1)
-    assert int(fast.status.abs().sum()) == 0
+        one = B.fixed_point(Ad, Bd, left=left, want_vec=False)   # one-kernel warp-per-problem form (kernels_fp64w.cuh)
+        one32 = B.fixed_point(Ad.to(t.complex64), Bd.to(t.complex64), left=left, want_vec=False)
+    finally:
+        lib.qmps_set_option(b"fp64_fast", 2)
+    assert int(fast.status.abs().sum()) == 0 and int(one.status.abs().sum()) == 0
     assert (fast.eta - slow.eta).abs().max().item() < 1e-12
+    assert (one.eta - slow.eta).abs().max().item() < 1e-12
+    assert (one32.eta.abs().double() - fast.eta.abs()).abs().max().item() < 1e-5
     for k in range(count):
         E = sum(np.kron(A[k, s], Bt[k, s].conj()) for s in range(d))
         w = np.linalg.eigvals(E)
@@ -419,19 +424,19 @@ def test_fixed_point_d8_degenerate_inputs(env):
     X = t.from_numpy(np.concatenate([A, prod, zero, blk])).cuda()
     lib = env["L"].load()
     res = {}
-    for fast in (0, 1):
+    for fast in (0, 1, 2):
         lib.qmps_set_option(b"fp64_fast", fast)
         try:
             fp = B.fixed_point(X, X, want_vec=False)
             res[fast] = fp.eta.cpu().numpy()
             assert int(fp.status.abs().sum().item()) == 0
         finally:
-            lib.qmps_set_option(b"fp64_fast", 1)
+            lib.qmps_set_option(b"fp64_fast", 2)
         eta = res[fast]
         assert np.abs(np.abs(eta[:3]) - 1).max() < 1e-12
         assert abs(abs(eta[3]) - 1) < 1e-12 and abs(eta[4]) == 0
         assert abs(abs(eta[5]) - 1) < 1e-12                    # the leading block is an isometry with itself
-    assert np.abs(np.abs(res[0]) - np.abs(res[1])).max() < 1e-12
+    assert np.abs(np.abs(res[0]) - np.abs(res[1])).max() < 1e-12 and np.abs(np.abs(res[0]) - np.abs(res[2])).max() < 1e-12
 
 
 def test_fixed_point_outer_and_broadcast(env):

@@ -31,7 +31,7 @@ def main():
                 ref.append(np.abs(w).max())
             ref = np.array(ref)
             out = {}
-            for fast in (0, 1):
+            for fast in (0, 1, 2):
                 lib.qmps_set_option(b"fp64_fast", fast)
                 res = B.fixed_point(torch.from_numpy(A).to(dev), torch.from_numpy(Bt).to(dev), left=left, want_vec=False)
                 eta = res.eta
@@ -39,7 +39,7 @@ def main():
             print(json.dumps({"check": "haar_pairs", "d": d, "left": left,
                               "max_rel_abs_eta_vs_numpy": float(np.max(np.abs(np.abs(out[1]) - ref) / ref)),
                               "generic_vs_numpy": float(np.max(np.abs(np.abs(out[0]) - ref) / ref)),
-                              "max_abs_eta_fast_vs_generic": float(np.max(np.abs(out[1] - out[0])))}), flush=True)
+                              "max_abs_eta_fast_vs_generic": float(np.max(np.abs(out[1] - out[0]))), "max_abs_eta_packed_vs_generic": float(np.max(np.abs(out[2] - out[0])))}), flush=True)
     # --- the bench tile
     NP, NT = int(os.environ.get("NP", 256)), int(os.environ.get("NT", 100))
     theta = torch.from_numpy(np.random.default_rng(8).normal(size=(NP, 24))).to(dev)
@@ -51,7 +51,7 @@ def main():
     for cdt, tag in ((torch.complex128, "c128"), (torch.complex64, "c64")):
         A0 = B.ansatz_tensors(prog, theta[:1], dtype=cdt)[0]
         W = torch.from_numpy(Wn).to(dev).to(cdt)
-        for fast in (0, 1):
+        for fast in (0, 1, 2):
             lib.qmps_set_option(b"fp64_fast", fast)
             fn = lambda: B.loschmidt_costs(prog, theta, A0, W, dtype=cdt)
             lib.qmps_debug_counters(cnt, 1)
@@ -70,7 +70,7 @@ def main():
             print(json.dumps({"dtype": tag, "fp64_fast": fast, "ms": round(ms, 3), "steps_per_s": NP * NT / ms * 1e3,
                               "max_abs_diff_vs_generic_c128": err,
                               "sweeps_per_problem": cnt[1] / max(cnt[0], 1), "forced": int(cnt[2])}), flush=True)
-    lib.qmps_set_option(b"fp64_fast", 1)
+    lib.qmps_set_option(b"fp64_fast", 2)
 
 
 if __name__ == "__main__":
