@@ -8,8 +8,8 @@
 // which 1.6 are fixed-latency dependency stalls and 0.7 shared-memory round trips -- the QR sweep is a dependent chain
 // and only more warps hide it.  The 65 KB are needed by the Householder reduction alone: the QR phase works on an
 // upper Hessenberg matrix, 2143 of 4096 entries.  So:
-//   fp64p_hess_kernel   builds E and reduces it (full padded tile, three warps per SM; throughput-bound, 14 % of the
-//                       work) and writes the Hessenberg matrix PACKED to a global workspace (34 KB per problem);
+//   fp64p_hess_kernel   builds E and reduces it (full padded tile, a CTA of 64 threads per problem, three per SM;
+//                       throughput work) and writes the Hessenberg matrix PACKED to a global workspace (34 KB each);
 //   fp64p_qr_kernel     loads the packed matrix (linear, coalesced) into 34 KB of shared memory -- SIX warps per SM
 //                       in complex128, twelve in complex64 -- and runs the sweeps of kernels_fp64w.cuh on it.
 // Packed layout: 32 lines of 67 entries; line q holds row q (columns q-1..63, 65-q entries, from the front) and row
@@ -38,26 +38,115 @@ template <typename T> QMPS_HD Fp64pLayout<T> fp64p_layout() {
 }
 
 // ---- kernel 1: E -> Hessenberg -> packed global workspace --------------------------------------------------------
-// problems [p.pid_offset, p.pid_offset + p.n_chunk) of the batch; workspace slot = pid - p.pid_offset
+// problems [p.pid_offset, p.pid_offset + p.n_chunk) of the batch; workspace slot = pid - p.pid_offset.
+// The reduction is throughput work (independent columns in the left update, independent rows in the right one), and with
+// one warp per problem it ran at a dependent-FMA latency per row (33 of the 59 ms of the first packed version): here a
+// CTA of 64 threads owns the problem, thread t = column t (left) / row t (right), dot products on two accumulators.
 template <typename T>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 fp64p_hess_kernel(FpParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Fp64wLayout<T> L = fp64w_layout<T>();
-  const int ln = threadIdx.x & 31, l32 = ln + 32;
+  const int t = threadIdx.x;
   cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw + L.S);
   cx<T>* vv = reinterpret_cast<cx<T>*>(smem_raw + L.rot);
-  for (int64_t k = blockIdx.x; k < p.n_chunk; k += gridDim.x) {
-    fp64w_build_hessenberg<T>(p, p.pid_offset + k, S, vv, ln);
-    cx<T>* __restrict__ W = reinterpret_cast<cx<T>*>(p.ws) + (size_t)k * F64P_SIZE;
-#pragma unroll 4
-    for (int r = 0; r < F64_N; ++r) {
-      const int base = f64p_row(r);
-      if (ln >= r - 1) W[base + ln] = S[F64S(r, ln)];
-      if (l32 >= r - 1) W[base + l32] = S[F64S(r, l32)];
+  T* red = reinterpret_cast<T*>(vv + F64_N);                     // two partial norms (the rotation table has 130 entries)
+  const int d = p.d;
+  const size_t tsz = (size_t)d * F64_N;
+  for (int64_t kk = blockIdx.x; kk < p.n_chunk; kk += gridDim.x) {
+    const int64_t pid = p.pid_offset + kk;
+    int64_t ia, ib;
+    if (p.pair_mode == 1) { ia = pid / p.NB; ib = pid - ia * p.NB; }
+    else if (p.pair_mode == 2) { ib = pid / p.NA; ia = pid - ib * p.NA; }
+    else { ia = pid < p.NA ? pid : p.NA - 1; ib = pid < p.NB ? pid : p.NB - 1; }
+    const cx<T>* __restrict__ Ag = reinterpret_cast<const cx<T>*>(p.A) + ia * tsz;
+    const cx<T>* __restrict__ Bg = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;
+    // ---- column t = (jj, ll) of E (E^dagger for the left fixed point), eight rows (i, 0..7) at a time
+    {
+      const int jj = t >> 3, ll = t & 7;
+      const int sa = p.left ? 1 : 8;
+      const int oa = p.left ? jj * 8 : jj, ob = p.left ? ll * 8 : ll;
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        cx<T> acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = mk<T>(0, 0);
+#pragma unroll 1
+        for (int s = 0; s < d; ++s) {
+          const cx<T> a = Ag[s * 64 + i * sa + oa];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cmad_c(acc[k], a, Bg[s * 64 + k * sa + ob]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (p.left) acc[k].im = -acc[k].im;
+          S[F64S(i * 8 + k, t)] = acc[k];
+        }
+      }
     }
-    if (ln == 0) W[0] = mk<T>(0, 0);                             // the one unused slot (row 0 has no column -1)
-    __syncwarp();
+    __syncthreads();
+    // ---- Householder reduction to Hessenberg form, in place
+#pragma unroll 1
+    for (int k = 0; k + 2 < F64_N; ++k) {
+      const cx<T> xk = S[F64S(t, k)];                             // column k, my row
+      const cx<T> alpha = S[F64S(k + 1, k)];
+      T part = (t > k + 1) ? norm2(xk) : T(0);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+      if ((t & 31) == 0) red[t >> 5] = part;
+      __syncthreads();
+      const T xn2 = red[0] + red[1];
+      if ((xn2 == T(0)) && (alpha.im == T(0))) { __syncthreads(); continue; }   // already reduced (CTA-uniform)
+      T beta = sqrt(norm2(alpha) + xn2);
+      if (alpha.re > T(0)) beta = -beta;
+      const T ibeta = T(1) / beta;
+      const cx<T> tau = mk<T>((beta - alpha.re) * ibeta, -alpha.im * ibeta);
+      const cx<T> scal = cinv(alpha - mk<T>(beta, 0));
+      cx<T> v = mk<T>(0, 0);                                      // my component of the scaled reflector (v[k+1] = 1)
+      if (t == k + 1) v = mk<T>(1, 0);
+      else if (t > k + 1) v = xk * scal;
+      vv[t] = v;
+      if (t == k + 1) S[F64S(t, k)] = mk<T>(beta, 0);
+      else if (t > k + 1) S[F64S(t, k)] = mk<T>(0, 0);
+      __syncthreads();
+      // left:  H <- (1 - conj(tau) v v^H) H on my column (columns <= k have nothing to update)
+      if (t > k) {
+        cx<T> w0 = mk<T>(0, 0), w1 = mk<T>(0, 0);
+        int i = k + 1;
+#pragma unroll 2
+        for (; i + 1 < F64_N; i += 2) {
+          cmad(w0, conj(vv[i]), S[F64S(i, t)]);
+          cmad(w1, conj(vv[i + 1]), S[F64S(i + 1, t)]);
+        }
+        if (i < F64_N) cmad(w0, conj(vv[i]), S[F64S(i, t)]);
+        const cx<T> w = (w0 + w1) * conj(tau);
+#pragma unroll 4
+        for (int r = k + 1; r < F64_N; ++r) { cx<T> h = S[F64S(r, t)]; cmsub(h, vv[r], w); S[F64S(r, t)] = h; }
+      }
+      __syncthreads();
+      // right: H <- H (1 - tau v v^H) on my row
+      {
+        cx<T> u0 = mk<T>(0, 0), u1 = mk<T>(0, 0);
+        int j = k + 1;
+#pragma unroll 2
+        for (; j + 1 < F64_N; j += 2) {
+          cmad(u0, S[F64S(t, j)], vv[j]);
+          cmad(u1, S[F64S(t, j + 1)], vv[j + 1]);
+        }
+        if (j < F64_N) cmad(u0, S[F64S(t, j)], vv[j]);
+        const cx<T> u = (u0 + u1) * tau;
+#pragma unroll 4
+        for (int c = k + 1; c < F64_N; ++c) { cx<T> h = S[F64S(t, c)]; cmsub(h, u, conj(vv[c])); S[F64S(t, c)] = h; }
+      }
+      __syncthreads();
+    }
+    // ---- pack: row r, columns r-1..63
+    cx<T>* __restrict__ W = reinterpret_cast<cx<T>*>(p.ws) + (size_t)kk * F64P_SIZE;
+#pragma unroll 4
+    for (int r = 0; r < F64_N; ++r)
+      if (t >= r - 1) W[f64p_row(r) + t] = S[F64S(r, t)];
+    if (t == 0) W[0] = mk<T>(0, 0);                              // the one unused slot (row 0 has no column -1)
+    __syncthreads();
   }
 }
 

@@ -278,7 +278,7 @@ def _roof(bound, achieved, peak, unit, kernel, per_unit, note=None, traffic=None
 
 def leg_loschmidt(torch, B, R, dev, D, peaks, scale=1.0, c64_too=True):
     """cfg 7 (D = 2) / cfg 3 (D = 4): 4096 parameter sets x 1000 times, one qmps_loschmidt_batched call; D = 8 (the metric's
-    middle bond dimension; 64 x 64 mixed maps on the generic group kernel): 256 parameter sets x 100 times."""
+    middle bond dimension; 64 x 64 mixed maps on the packed warp-per-problem kernels): 256 parameter sets x 100 times."""
     NP, NT = max(64, int(4096 * scale)), 1000
     if D == 2:
         P, seed, gate = 15, 7, R.ShallowFullStateTensor(2, np.zeros(15))
@@ -303,7 +303,7 @@ def leg_loschmidt(torch, B, R, dev, D, peaks, scale=1.0, c64_too=True):
            "value": units / ms * 1e3, "ms_per_step": ms, "units_per_step": units,
            "api": "qmps_loschmidt_batched (ansatz, merge, gate-merge, fixed points; 4 launches)",
            "roofline": _roof("fp64", units * flops / ms * 1e3 / 1e12, peaks["fp64_fma_tflops"], "TFLOP/s",
-                             {2: "fp_d2_kernel<double>", 4: "fp16s8_kernel<double>", 8: "fixed_point_kernel<double,128>"}[D], f"{flops:.3g} real flops (100 n^3, n = {n})",
+                             {2: "fp_d2_kernel<double>", 4: "fp16s8_kernel<double>", 8: "fp64p_hess_kernel<double> + fp64p_qr_kernel<double>"}[D], f"{flops:.3g} real flops (100 n^3, n = {n})",
                              note="eigenvalues of every map by Hessenberg + shifted QR; iteration counts are data dependent, "
                                   "the algorithmic count is the LAPACK-style estimate")}
     if c64_too:
