@@ -79,7 +79,7 @@ const char* qmps_last_error(void);
  * D = 2 streaming kernel, default 1), "d2_ctas_per_sm" (resident CTAs per SM of that kernel, default 1 = measured best; 0: occupancy limit),
  * "fp16_fast" (the D = 4 eigenvalue-only kernel: 0 generic shared-memory group kernel, 1-5 register-resident
  * half / quarter-warp forms, 6 / 7 shared-resident half / quarter warp, 8 = 7 with a branch-free reciprocal square
- * root, default 8 = measured best, see profiles/README.md), "fp64_fast" (the D = 8 eigenvalue-only path: 0 generic
+ * root, 9 packed two-kernel form, 10 = 8 with trimmed sweep bodies, default 8 = measured best, see profiles/README.md), "fp64_fast" (the D = 8 eigenvalue-only path: 0 generic
  * CTA-per-problem kernel, 1 one warp per 64 x 64 map, 2 packed two-kernel form, default 2 = measured best),
  * "env_real" (1: the real-form register-resident D = 4, 8 direct solver, default 1; 0: generic kernel). */
 int qmps_set_option(const char* name, int value);

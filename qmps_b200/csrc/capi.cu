@@ -16,7 +16,7 @@ static_assert(QMPS_G_YYPOW == G_YYPOW && QMPS_G_Z == G_Z, "gate codes");
 
 namespace qmps_host {
 std::string& last_error() { thread_local std::string e; return e; }
-static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 8 /* fp16_fast: D = 4 eigenvalue-only kernel; 0 generic, 1/2 half-warp registers, 3-5 quarter-warp registers, 6 shared-resident, 7 shared-resident quarter-warp, 8 the same with a branch-free reciprocal square root in the sweep body (measured best: profiles/exp_fp16_r02n.jsonl) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */, 1 /* i8_power: complex128 D % 64 == 0 on tcgen05 kind::i8 (0: FP64 tensor pipe) */, -1 /* tc_presplit: complex64 slab images carry hi + lo planes (1), fp32 split in shared memory (0), by size (-1) */, 2 /* fp64_fast: D = 8 eigenvalue-only path; 0 generic CTA-per-problem kernel, 1 one warp per 64 x 64 map (kernels_fp64w.cuh), 2 packed two-kernel form (kernels_fp64p.cuh; measured best: profiles/exp_fp64w_r02n.jsonl) */};
+static int g_options[OPT_COUNT] = {1 /* d2_pdl */, 1 /* d2_ctas_per_sm (measured best: profiles/sweep_d2_r01.jsonl); 0 = occupancy */, 8 /* fp16_fast: D = 4 eigenvalue-only kernel; 0 generic, 1/2 half-warp registers, 3-5 quarter-warp registers, 6 shared-resident, 7 shared-resident quarter-warp, 8 the same with a branch-free reciprocal square root in the sweep body (measured best: profiles/exp_fp16_r02n.jsonl), 9 packed two-kernel form, 10 trimmed sweep bodies (both measured equal or slower: profiles/exp_fp16_r02q/r.jsonl) */, 1 /* env_real */, 1 /* tc_power: complex64 D % 64 == 0 on tcgen05 */, 1 /* tc_persistent */, 0, 0, -1 /* er_wide: auto */, 1 /* fp_d2: thread-per-problem D = 2 eigenvalue path */, 1 /* bw_thread: thread-per-candidate brick-wall cost */, 1 /* i8_power: complex128 D % 64 == 0 on tcgen05 kind::i8 (0: FP64 tensor pipe) */, -1 /* tc_presplit: complex64 slab images carry hi + lo planes (1), fp32 split in shared memory (0), by size (-1) */, 2 /* fp64_fast: D = 8 eigenvalue-only path; 0 generic CTA-per-problem kernel, 1 one warp per 64 x 64 map (kernels_fp64w.cuh), 2 packed two-kernel form (kernels_fp64p.cuh; measured best: profiles/exp_fp64w_r02n.jsonl) */};
 std::unordered_map<LaunchKey, int, LaunchKeyHash>& occupancy_cache() { static std::unordered_map<LaunchKey, int, LaunchKeyHash> c; return c; }
 std::mutex& occupancy_mutex() { static std::mutex m; return m; }
 int option_get(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }

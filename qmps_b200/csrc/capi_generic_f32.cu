@@ -4,6 +4,7 @@
 #include "launch_envreal.cuh"
 #include "kernels_fp16x8.cuh"
 #include "kernels_fp16s.cuh"
+#include "kernels_fp16p.cuh"
 #include "kernels_fp64w.cuh"
 #include "kernels_fp64p.cuh"
 #include "kernels_fpd2.cuh"
@@ -93,17 +94,43 @@ int launch_fp16s(FpParams p, cudaStream_t st) {
   CK(cudaGetLastError());
   return 0;
 }
-template <bool FASTRSQ> int launch_fp16s8(FpParams p, cudaStream_t st) {
+template <bool FASTRSQ, bool TRIM = false> int launch_fp16s8(FpParams p, cudaStream_t st) {
   const Fp16sLayout<REAL> L = fp16s_layout<REAL>();
   const int block = 64, gpc = block / 8;
   const size_t smem = L.total * gpc;
-  auto kern = fp16s8_kernel<REAL, FASTRSQ>;
+  auto kern = fp16s8_kernel<REAL, FASTRSQ, TRIM>;
   if (int rc = allow_smem(kern, smem)) return rc;
   int grid = 1;
   if (int rc = persistent_grid(kern, block, smem, (p.N + gpc - 1) / gpc, &grid)) return rc;
   p.ws = nullptr; p.ws_stride = 0;
   kern<<<grid, block, smem, st>>>(p);
   CK(cudaGetLastError());
+  return 0;
+}
+// packed two-kernel form (kernels_fp16p.cuh): Hessenberg reduction -> packed workspace -> QR with 18 warps per SM
+int launch_fp16p(FpParams p, cudaStream_t st) {
+  const int64_t CH = 1 << 20;                                  // problems per launch pair: 2.4 KB (complex128) of workspace each
+  const int64_t nws = p.N < CH ? p.N : CH;
+  const int block = 64, gpc = block / 8;
+  const size_t smem_h = fp16s_layout<REAL>().total * gpc, smem_q = fp16p_layout<REAL>().total * gpc;
+  auto kh = fp16p8_kernel<REAL, 1>;
+  auto kq = fp16p8_kernel<REAL, 2>;
+  if (int rc = allow_smem(kh, smem_h)) return rc;
+  if (int rc = allow_smem(kq, smem_q)) return rc;
+  void* ws = nullptr;
+  CK(malloc_async(&ws, sizeof(cx<REAL>) * (size_t)F16P_SIZE * nws, st));
+  p.ws = ws; p.ws_stride = F16P_SIZE;
+  for (int64_t off = 0; off < p.N; off += CH) {
+    p.pid_offset = off; p.n_chunk = p.N - off < CH ? p.N - off : CH;
+    int gh = 1, gq = 1;
+    if (int rc = persistent_grid(kh, block, smem_h, (p.n_chunk + gpc - 1) / gpc, &gh)) { cudaFreeAsync(ws, st); return rc; }
+    if (int rc = persistent_grid(kq, block, smem_q, (p.n_chunk + gpc - 1) / gpc, &gq)) { cudaFreeAsync(ws, st); return rc; }
+    kh<<<gh, block, smem_h, st>>>(p);
+    kq<<<gq, block, smem_q, st>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  CK(e);
   return 0;
 }
 // option fp16_fast: 6 = shared-resident form, 7 = its quarter-warp variant; 1 / 2 = half-warp form with the register budget of 3 / 4 CTAs per SM;
@@ -116,7 +143,9 @@ int launch_fp16(const FpParams& p, cudaStream_t st) {
     case 5: return launch_fp16x8_v<6>(p, st);
     case 6: return launch_fp16s(p, st);
     case 7: return launch_fp16s8<false>(p, st);
-    case 8: return launch_fp16s8<true>(p, st);      // + branch-free reciprocal square root in the sweep body
+    case 8: return launch_fp16s8<true>(p, st);
+    case 9: return launch_fp16p(p, st);             // packed two-kernel form of 8
+    case 10: return launch_fp16s8<true, true>(p, st); // 8 with the trimmed sweep bodies      // + branch-free reciprocal square root in the sweep body
     default: return launch_fp16_v<3>(p, st);
   }
 }

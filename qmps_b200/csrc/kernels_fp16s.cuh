@@ -261,7 +261,44 @@ fp16s_kernel(FpParams p) {
 // instructions of a step in the half-warp form, profiles/ncu_fp16_r02e.txt) is shared by four problems
 // instead of two, and structural zeros are skipped: columns 0..7 have nothing below row 8, rows 8..15
 // nothing left of column 7.
-template <typename T, bool FASTRSQ = false>
+// One left-phase step of fp16s8_kernel<T, FASTRSQ, TRIM = true>: rotation i (rows (i-1, i)) on my columns q (LOW: while
+// i <= 8) and q + 8.  LOW also says which half holds column i - 1, whose owner lane generates the rotation.
+template <typename T, bool LOW>
+__device__ __forceinline__ void fp16s8_left_step(cx<T>* S, cx<T>* rot, int q, int q8, int i, int hi, bool busy, int lw, int enw,
+                                                 cx<T>& pa, cx<T>& pb, cx<T>& qa, cx<T>& qb) {
+  const int in = i + 1 <= hi ? i + 1 : hi;
+  cx<T> qa_n = mk<T>(0, 0);
+  if (LOW && in <= 8) qa_n = S[F16S(in, q)];
+  const cx<T> qb_n = S[F16S(in, q8)];
+  const bool act = busy && (i > lw) && (i <= enw);
+  const cx<T> f = LOW ? pa : pb, g = LOW ? qa : qb;
+  const T nr2 = norm2(f) + norm2(g);
+  const bool ok = act && nr2 > T(0);
+  const T y = rsq_fast<T>(nr2);
+  const T inr = ok ? y : T(0);                                 // identity rotation outside my window / for a zero pair
+  cx<T> c, s;
+  c.re = fma_t(f.re, inr, ok ? T(0) : T(1)); c.im = f.im * inr;
+  s.re = g.re * inr; s.im = g.im * inr;
+  const int src = (i - 1) & 7;
+  const bool owner = q == src;
+  if (owner) { rot[2 * i] = c; rot[2 * i + 1] = s; }
+  c.re = __shfl_sync(0xffffffffu, c.re, src, 8); c.im = __shfl_sync(0xffffffffu, c.im, src, 8);
+  s.re = __shfl_sync(0xffffffffu, s.re, src, 8); s.im = __shfl_sync(0xffffffffu, s.im, src, 8);
+  cx<T> top = conj(c) * pb; cmad(top, conj(s), qb);
+  cx<T> bot = c * qb; cmsub(bot, s, pb);
+  if (LOW) {
+    cx<T> ta = conj(c) * pa; cmad(ta, conj(s), qa);
+    cx<T> ba = c * qa; cmsub(ba, s, pa);
+    if (ok && owner) ba = mk<T>(0, 0);
+    S[F16S(i - 1, q)] = ta;
+    pa = ba;
+  } else if (ok && owner) bot = mk<T>(0, 0);
+  S[F16S(i - 1, q8)] = top;
+  pb = bot;
+  qa = qa_n; qb = qb_n;
+}
+
+template <typename T, bool FASTRSQ = false, bool TRIM = false>
 __global__ void __launch_bounds__(64, 6)
 fp16s8_kernel(FpParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -430,6 +467,56 @@ fp16s8_kernel(FpParams p) {
       if (win_b) S[F16S(q8, q8)] = S[F16S(q8, q8)] - sigma;
       if (busy && lw >= 1 && q == 0) S[F16S(lw, lw - 1)] = mk<T>(0, 0);
       __syncwarp();
+      if constexpr (TRIM) {
+        // the same two phases with fewer issued instructions (the kernel is issue-bound: ~66 % of the issue slots at cfg 3's
+        // size): loops cut at row / column 8 so that the half of the owner lane is a compile-time fact, identity rotations
+        // by a zeroed scale instead of eight selects, the exact zero of the annihilated entry kept but not the exact
+        // modulus of its partner, bodies unrolled by two
+        {
+          cx<T> pa = S[F16S(lo < 8 ? lo : 8, q)], pb = S[F16S(lo, q8)];
+          cx<T> qa = mk<T>(0, 0), qb = S[F16S(lo + 1 <= hi ? lo + 1 : hi, q8)];
+          if (lo + 1 <= 8) qa = S[F16S(lo + 1 <= hi ? lo + 1 : hi, q)];
+          int i = lo + 1;
+          const int e1 = hi < 8 ? hi : 8;
+#pragma unroll 2
+          for (; i <= e1; ++i) fp16s8_left_step<T, true>(S, rot, q, q8, i, hi, busy, lw, enw, pa, pb, qa, qb);
+#pragma unroll 2
+          for (; i <= hi; ++i) fp16s8_left_step<T, false>(S, rot, q, q8, i, hi, busy, lw, enw, pa, pb, qa, qb);
+          if (lo < 8) S[F16S(hi < 8 ? hi : 8, q)] = pa;
+          S[F16S(hi, q8)] = pb;
+        }
+        __syncwarp();
+        {
+          cx<T> xa = S[F16S(q, lo)];
+          const int j8 = lo + 1 > 8 ? lo + 1 : 8;             // first rotation that touches rows >= 8
+          cx<T> xb = S[F16S(q8, j8 - 1)];
+          int j = lo + 1;
+          const int e1 = hi < 7 ? hi : 7;
+#pragma unroll 2
+          for (; j <= e1; ++j) {
+            const cx<T> c = rot[2 * j], s = rot[2 * j + 1];
+            const cx<T> ya = S[F16S(q, j)];
+            cx<T> a = xa * c; cmad(a, ya, s);
+            cx<T> b = ya * conj(c); cmsub(b, xa, conj(s));
+            S[F16S(q, j - 1)] = a;
+            xa = b;
+          }
+#pragma unroll 2
+          for (; j <= hi; ++j) {
+            const cx<T> c = rot[2 * j], s = rot[2 * j + 1];
+            const cx<T> ya = S[F16S(q, j)], yb = S[F16S(q8, j)];
+            cx<T> a = xa * c; cmad(a, ya, s);
+            cx<T> b = ya * conj(c); cmsub(b, xa, conj(s));
+            cx<T> a2 = xb * c; cmad(a2, yb, s);
+            cx<T> b2 = yb * conj(c); cmsub(b2, xb, conj(s));
+            S[F16S(q, j - 1)] = a;
+            S[F16S(q8, j - 1)] = a2;
+            xa = b; xb = b2;
+          }
+          S[F16S(q, hi)] = xa;
+          if (hi >= 8) S[F16S(q8, hi)] = xb;
+        }
+      } else {
       // left phase.  Column q is carried in pa (rows <= 8 only), column q + 8 in pb.
       {
         cx<T> pa = S[F16S(lo < 8 ? lo : 8, q)], pb = S[F16S(lo, q8)];
@@ -497,6 +584,7 @@ fp16s8_kernel(FpParams p) {
         }
         S[F16S(q, hi)] = xa;
         if (hi >= 8) S[F16S(q8, hi)] = xb;
+      }
       }
       if (win_a) S[F16S(q, q)] = S[F16S(q, q)] + sigma;
       if (win_b) S[F16S(q8, q8)] = S[F16S(q8, q8)] + sigma;

@@ -279,7 +279,7 @@ def test_fixed_point_d4_eigenvalue_only_kernel(env, left, d):
     finally:
         lib.qmps_set_option(b"fp16_fast", 8)
     assert (default.eta.abs() - slow.eta.abs()).abs().max().item() < TOL
-    for variant in (1, 3, 6, 7, 8):    # half-warp / quarter-warp register forms, shared-resident half / quarter warp (8: branch-free rsqrt)
+    for variant in (1, 3, 6, 7, 8, 9, 10):  # half-warp / quarter-warp register forms, shared-resident half / quarter warp (8: branch-free rsqrt, 9: packed two-kernel form, 10: trimmed sweep bodies)
         lib.qmps_set_option(b"fp16_fast", variant)
         try:
             fast = B.fixed_point(Ad, Bd, left=left, want_vec=False)
@@ -352,7 +352,7 @@ def test_fixed_point_d4_degenerate_inputs(env):
     zero = np.zeros((1, 2, 4, 4), complex)
     X = t.from_numpy(np.concatenate([A, prod, zero])).cuda()
     lib = env["L"].load()
-    for fast in (0, 1, 3, 6, 7, 8):
+    for fast in (0, 1, 3, 6, 7, 8, 9, 10):
         lib.qmps_set_option(b"fp16_fast", fast)
         try:
             fp = B.fixed_point(X, X, want_vec=False)
