@@ -64,6 +64,12 @@ template <> __device__ __forceinline__ double rsq_fast<double>(double x) {
   return y;
 }
 template <> __device__ __forceinline__ float rsq_fast<float>(float x) { return rsqrtf(x); }
+// smallest squared modulus rsq_fast is used on: the MUFU seed flushes subnormal inputs (rsqrt of zero = inf, then NaN in the
+// Newton step), so a pair below this is treated as a zero pair (identity rotation) -- it is below 1e-140 (1e-17 in
+// complex64) in modulus and far beneath the negligibility threshold of any matrix the sweeps see
+template <typename T> struct rsq_floor;
+template <> struct rsq_floor<double> { static __device__ __forceinline__ double v() { return 1e-280; } };
+template <> struct rsq_floor<float> { static __device__ __forceinline__ float v() { return 1e-34f; } };
 
 template <typename T> __device__ __forceinline__ cx<T> shfl16(cx<T> v, int src) {
   cx<T> r;

@@ -240,7 +240,7 @@ fp16p8_kernel(FpParams p) {
           const bool act = busy && (i > lw) && (i <= enw);
           const cx<T> f = low ? pa : pb, g = low ? qa : qb;  // column i-1 is an "a" column iff i-1 < 8
           const T nr2 = norm2(f) + norm2(g);
-          const bool ok = act && nr2 > T(0);
+          const bool ok = act && nr2 > rsq_floor<T>::v();
           const T inr = FASTRSQ ? rsq_fast<T>(nr2) : rsqrt_t<T>(nr2);   // FASTRSQ: no slow-path branch inside the sweep body
           cx<T> c = f * inr, s = g * inr;
           const T nr = nr2 * inr;

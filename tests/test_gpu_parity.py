@@ -439,6 +439,35 @@ def test_fixed_point_d8_degenerate_inputs(env):
     assert np.abs(np.abs(res[0]) - np.abs(res[1])).max() < 1e-12 and np.abs(np.abs(res[0]) - np.abs(res[2])).max() < 1e-12
 
 
+def test_fixed_point_packed_forms_chunked_workspace(env):
+    """The packed two-kernel forms work on slices of the batch (one workspace of at most 32 768 problems at D = 8, 2^20 at
+    D = 4): batches larger than one slice must give the same eigenvalues as the one-kernel forms, problem by problem
+    (outer pairing: problem index -> (ia, ib) goes through the slice offset)."""
+    t, B, O, L = env["torch"], env["B"], env["O"], env["L"]
+    lib = L.load()
+    A8, B8 = t.from_numpy(tensors(8, 190, 41, O)).cuda(), t.from_numpy(tensors(8, 180, 42, O)).cuda()      # 34 200 problems
+    try:
+        lib.qmps_set_option(b"fp64_fast", 2)
+        packed = B.fixed_point(A8, B8, pair="outer", want_vec=False)
+        lib.qmps_set_option(b"fp64_fast", 1)
+        one = B.fixed_point(A8, B8, pair="outer", want_vec=False)
+    finally:
+        lib.qmps_set_option(b"fp64_fast", 2)
+    assert int(packed.status.abs().sum()) == 0
+    assert (packed.eta - one.eta).abs().max().item() < 1e-12
+    assert (packed.cost - one.cost).abs().max().item() < 1e-12
+    A4, B4 = t.from_numpy(tensors(4, 1030, 43, O)).cuda(), t.from_numpy(tensors(4, 1020, 44, O)).cuda()    # 1 050 600 problems
+    try:
+        lib.qmps_set_option(b"fp16_fast", 9)
+        packed = B.fixed_point(A4, B4, pair="outer", want_vec=False)
+        lib.qmps_set_option(b"fp16_fast", 8)
+        one = B.fixed_point(A4, B4, pair="outer", want_vec=False)
+    finally:
+        lib.qmps_set_option(b"fp16_fast", 8)
+    assert int(packed.status.abs().sum()) == 0
+    assert (packed.eta - one.eta).abs().max().item() < 1e-12
+
+
 def test_fixed_point_outer_and_broadcast(env):
     t, B, O = env["torch"], env["B"], env["O"]
     A, Bt = tensors(2, 3, 1, O), tensors(2, 5, 2, O)

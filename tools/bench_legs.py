@@ -475,7 +475,7 @@ def leg_tdvp_large(torch, B, dev, peaks, D=64, N=64):
         out = B.tdvp_tangent_large(A, h)
         info.update(out[2])
         return out
-    ms = timed_ms(torch, fn, reps=2, warm=1)
+    ms = timed_ms(torch, fn, reps=3, warm=2)
     d = 2
     gemms = 5 * d * d + 4 * d + 2 * d * info["k_iterations"] + 2 * d * (info["r_iterations"] + 1)
     flops = gemms * 8.0 * D ** 3
