@@ -168,7 +168,7 @@ int launch_fp64w(FpParams p, cudaStream_t st) {
 int launch_fp64p(FpParams p, cudaStream_t st) {
   const int64_t CH = 32768;                                    // problems per launch pair: 34 KB (complex128) of workspace each, 1.1 GB at most
   const int64_t nws = p.N < CH ? p.N : CH;
-  const size_t smem_h = fp64w_layout<REAL>().total, smem_q = fp64p_layout<REAL>().total;
+  const size_t smem_h = fp64w_layout<REAL>().total + sizeof(cx<REAL>) * 2 * F64_N, smem_q = fp64p_layout<REAL>().total;
   auto kh = fp64p_hess_kernel<REAL>;
   auto kq = fp64p_qr_kernel<REAL>;
   if (int rc = allow_smem(kh, smem_h)) return rc;
@@ -179,9 +179,9 @@ int launch_fp64p(FpParams p, cudaStream_t st) {
   for (int64_t off = 0; off < p.N; off += CH) {
     p.pid_offset = off; p.n_chunk = p.N - off < CH ? p.N - off : CH;
     int gh = 1, gq = 1;
-    if (int rc = persistent_grid(kh, 64, smem_h, p.n_chunk, &gh)) { cudaFreeAsync(ws, st); return rc; }
+    if (int rc = persistent_grid(kh, 128, smem_h, p.n_chunk, &gh)) { cudaFreeAsync(ws, st); return rc; }
     if (int rc = persistent_grid(kq, 32, smem_q, p.n_chunk, &gq)) { cudaFreeAsync(ws, st); return rc; }
-    kh<<<gh, 64, smem_h, st>>>(p);
+    kh<<<gh, 128, smem_h, st>>>(p);
     kq<<<gq, 32, smem_q, st>>>(p);
   }
   cudaError_t e = cudaGetLastError();

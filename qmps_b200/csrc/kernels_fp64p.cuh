@@ -41,16 +41,18 @@ template <typename T> QMPS_HD Fp64pLayout<T> fp64p_layout() {
 // problems [p.pid_offset, p.pid_offset + p.n_chunk) of the batch; workspace slot = pid - p.pid_offset.
 // The reduction is throughput work (independent columns in the left update, independent rows in the right one), and with
 // one warp per problem it ran at a dependent-FMA latency per row (33 of the 59 ms of the first packed version): here a
-// CTA of 64 threads owns the problem, thread t = column t (left) / row t (right), dot products on two accumulators.
+// CTA of 128 threads owns the problem: thread = (column t (left) / row t (right), half of the summation range), partial
+// dot products combined through shared memory, two accumulators each.
 template <typename T>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 fp64p_hess_kernel(FpParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Fp64wLayout<T> L = fp64w_layout<T>();
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x, t = tid & 63, hf = tid >> 6;     // thread = (column / row t, half hf of the summation range)
   cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw + L.S);
-  cx<T>* vv = reinterpret_cast<cx<T>*>(smem_raw + L.rot);
-  T* red = reinterpret_cast<T*>(vv + F64_N);                     // two partial norms (the rotation table has 130 entries)
+  cx<T>* vv = reinterpret_cast<cx<T>*>(smem_raw + L.rot);        // 64 reflector entries
+  T* red = reinterpret_cast<T*>(vv + F64_N);                     // 4 partial norms (one rotation-table slot = 2 reals x 2)
+  cx<T>* part = reinterpret_cast<cx<T>*>(smem_raw + L.total);    // 2 x 64 partial dot products (behind the one-kernel layout)
   const int d = p.d;
   const size_t tsz = (size_t)d * F64_N;
   for (int64_t kk = blockIdx.x; kk < p.n_chunk; kk += gridDim.x) {
@@ -61,13 +63,13 @@ fp64p_hess_kernel(FpParams p) {
     else { ia = pid < p.NA ? pid : p.NA - 1; ib = pid < p.NB ? pid : p.NB - 1; }
     const cx<T>* __restrict__ Ag = reinterpret_cast<const cx<T>*>(p.A) + ia * tsz;
     const cx<T>* __restrict__ Bg = reinterpret_cast<const cx<T>*>(p.B) + ib * tsz;
-    // ---- column t = (jj, ll) of E (E^dagger for the left fixed point), eight rows (i, 0..7) at a time
+    // ---- column t = (jj, ll) of E (E^dagger for the left fixed point); half hf builds rows (i, 0..7), i = 4 hf .. 4 hf + 3
     {
       const int jj = t >> 3, ll = t & 7;
       const int sa = p.left ? 1 : 8;
       const int oa = p.left ? jj * 8 : jj, ob = p.left ? ll * 8 : ll;
 #pragma unroll 1
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 4 * hf; i < 4 * hf + 4; ++i) {
         cx<T> acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = mk<T>(0, 0);
@@ -90,10 +92,10 @@ fp64p_hess_kernel(FpParams p) {
     for (int k = 0; k + 2 < F64_N; ++k) {
       const cx<T> xk = S[F64S(t, k)];                             // column k, my row
       const cx<T> alpha = S[F64S(k + 1, k)];
-      T part = (t > k + 1) ? norm2(xk) : T(0);
+      T pn = (hf == 0 && t > k + 1) ? norm2(xk) : T(0);
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-      if ((t & 31) == 0) red[t >> 5] = part;
+      for (int m = 16; m >= 1; m >>= 1) pn += __shfl_xor_sync(0xffffffffu, pn, m);
+      if ((tid & 31) == 0) red[tid >> 5] = pn;
       __syncthreads();
       const T xn2 = red[0] + red[1];
       if ((xn2 == T(0)) && (alpha.im == T(0))) { __syncthreads(); continue; }   // already reduced (CTA-uniform)
@@ -102,50 +104,63 @@ fp64p_hess_kernel(FpParams p) {
       const T ibeta = T(1) / beta;
       const cx<T> tau = mk<T>((beta - alpha.re) * ibeta, -alpha.im * ibeta);
       const cx<T> scal = cinv(alpha - mk<T>(beta, 0));
-      cx<T> v = mk<T>(0, 0);                                      // my component of the scaled reflector (v[k+1] = 1)
-      if (t == k + 1) v = mk<T>(1, 0);
-      else if (t > k + 1) v = xk * scal;
-      vv[t] = v;
-      if (t == k + 1) S[F64S(t, k)] = mk<T>(beta, 0);
-      else if (t > k + 1) S[F64S(t, k)] = mk<T>(0, 0);
+      if (hf == 0) {
+        cx<T> v = mk<T>(0, 0);                                    // my component of the scaled reflector (v[k+1] = 1)
+        if (t == k + 1) v = mk<T>(1, 0);
+        else if (t > k + 1) v = xk * scal;
+        vv[t] = v;
+        if (t == k + 1) S[F64S(t, k)] = mk<T>(beta, 0);
+        else if (t > k + 1) S[F64S(t, k)] = mk<T>(0, 0);
+      }
       __syncthreads();
+      // the summation range k+1 .. 63 in two halves
+      const int mid = (k + 1 + F64_N) >> 1;
+      const int lo = hf ? mid : k + 1, hi = hf ? F64_N : mid;
       // left:  H <- (1 - conj(tau) v v^H) H on my column (columns <= k have nothing to update)
-      if (t > k) {
+      {
         cx<T> w0 = mk<T>(0, 0), w1 = mk<T>(0, 0);
-        int i = k + 1;
+        if (t > k) {
+          int i = lo;
 #pragma unroll 2
-        for (; i + 1 < F64_N; i += 2) {
-          cmad(w0, conj(vv[i]), S[F64S(i, t)]);
-          cmad(w1, conj(vv[i + 1]), S[F64S(i + 1, t)]);
+          for (; i + 1 < hi; i += 2) {
+            cmad(w0, conj(vv[i]), S[F64S(i, t)]);
+            cmad(w1, conj(vv[i + 1]), S[F64S(i + 1, t)]);
+          }
+          if (i < hi) cmad(w0, conj(vv[i]), S[F64S(i, t)]);
         }
-        if (i < F64_N) cmad(w0, conj(vv[i]), S[F64S(i, t)]);
-        const cx<T> w = (w0 + w1) * conj(tau);
+        part[hf * F64_N + t] = w0 + w1;
+        __syncthreads();
+        if (t > k) {
+          const cx<T> w = (part[t] + part[F64_N + t]) * conj(tau);
 #pragma unroll 4
-        for (int r = k + 1; r < F64_N; ++r) { cx<T> h = S[F64S(r, t)]; cmsub(h, vv[r], w); S[F64S(r, t)] = h; }
+          for (int r = lo; r < hi; ++r) { cx<T> h = S[F64S(r, t)]; cmsub(h, vv[r], w); S[F64S(r, t)] = h; }
+        }
       }
       __syncthreads();
       // right: H <- H (1 - tau v v^H) on my row
       {
         cx<T> u0 = mk<T>(0, 0), u1 = mk<T>(0, 0);
-        int j = k + 1;
+        int j = lo;
 #pragma unroll 2
-        for (; j + 1 < F64_N; j += 2) {
+        for (; j + 1 < hi; j += 2) {
           cmad(u0, S[F64S(t, j)], vv[j]);
           cmad(u1, S[F64S(t, j + 1)], vv[j + 1]);
         }
-        if (j < F64_N) cmad(u0, S[F64S(t, j)], vv[j]);
-        const cx<T> u = (u0 + u1) * tau;
+        if (j < hi) cmad(u0, S[F64S(t, j)], vv[j]);
+        part[hf * F64_N + t] = u0 + u1;
+        __syncthreads();
+        const cx<T> u = (part[t] + part[F64_N + t]) * tau;
 #pragma unroll 4
-        for (int c = k + 1; c < F64_N; ++c) { cx<T> h = S[F64S(t, c)]; cmsub(h, u, conj(vv[c])); S[F64S(t, c)] = h; }
+        for (int c = lo; c < hi; ++c) { cx<T> h = S[F64S(t, c)]; cmsub(h, u, conj(vv[c])); S[F64S(t, c)] = h; }
       }
       __syncthreads();
     }
-    // ---- pack: row r, columns r-1..63
+    // ---- pack: row r, columns r-1..63 (half hf takes rows 32 hf .. 32 hf + 31)
     cx<T>* __restrict__ W = reinterpret_cast<cx<T>*>(p.ws) + (size_t)kk * F64P_SIZE;
 #pragma unroll 4
-    for (int r = 0; r < F64_N; ++r)
+    for (int r = 32 * hf; r < 32 * hf + 32; ++r)
       if (t >= r - 1) W[f64p_row(r) + t] = S[F64S(r, t)];
-    if (t == 0) W[0] = mk<T>(0, 0);                              // the one unused slot (row 0 has no column -1)
+    if (tid == 0) W[0] = mk<T>(0, 0);                            // the one unused slot (row 0 has no column -1)
     __syncthreads();
   }
 }
