@@ -330,6 +330,67 @@ QMPS_HDN int hqr_eigenvalues(const Grp& g, cx<T>* H, int ld, int n, cx<T>* w, cx
   return fail;
 }
 
+// ---- branch-free forms for the Wilkinson shift of the QR sweeps ------------------------------------------------
+// The shift needs a complex square root and a complex division per sweep: two IEEE square roots and two IEEE divisions,
+// each with a slow-path call on the device.  A shift only has to be the SAME number when it is subtracted and added
+// back, not a correctly rounded one, so on the device these use MUFU seeds + two Newton steps (an ulp or two) and no
+// branches; on the host (tests/host_emu) they are the exact forms above.
+QMPS_HD double rsq_nb(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+QMPS_HD float rsq_nb(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+QMPS_HD double rcp_nb(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(fma(-x, y, 1.0), y, y);
+  y = fma(fma(-x, y, 1.0), y, y);
+  return y;
+#else
+  return 1.0 / x;
+#endif
+}
+QMPS_HD float rcp_nb(float x) { return 1.0f / x; }
+template <typename T> struct nb_floor;
+template <> struct nb_floor<double> { static QMPS_HD double v() { return 1e-280; } };
+template <> struct nb_floor<float> { static QMPS_HD float v() { return 1e-34f; } };
+// sqrt(z), principal branch (same branch choice as csqrt); 0 for |z|^2 below the floor
+template <typename T> QMPS_HD cx<T> csqrt_nb(cx<T> z) {
+  const T n2 = norm2(z);
+  const bool ok = n2 > nb_floor<T>::v();
+  const T m = n2 * rsq_nb(ok ? n2 : T(1));                       // |z|
+  const T h = (m + fabs(z.re)) * T(0.5);                         // >= |z| / 2 > 0
+  const T ra = rsq_nb(ok ? h : T(1));
+  const T a = ok ? h * ra : T(0);                                // sqrt(h)
+  const T b = ok ? z.im * (T(0.5) * ra) : T(0);                  // z.im / (2 a)
+  cx<T> r;
+  r.re = z.re >= T(0) ? a : fabs(b);
+  r.im = z.re >= T(0) ? b : (z.im < T(0) ? -a : a);
+  return r;
+}
+// a / b; a itself times zero (i.e. 0) for |b|^2 below the floor -- the caller's shift then stays the corner entry
+template <typename T> QMPS_HD cx<T> cdiv_nb(cx<T> a, cx<T> b) {
+  const T n2 = norm2(b);
+  const bool ok = n2 > nb_floor<T>::v();
+  const T d = ok ? rcp_nb(ok ? n2 : T(1)) : T(0);
+  return a * mk<T>(b.re * d, -b.im * d);
+}
+
 // index of the eigenvalue of largest modulus (first one on ties)
 template <typename T> QMPS_HD int argmax_abs(const cx<T>* w, int n) {
   int k = 0;

@@ -79,7 +79,7 @@ template <typename T, int EN> QMPS_HD void fpd2_sweep(cx<T> (&H)[4][4], int l, c
       const T nr2 = norm2(f) + norm2(gg);
       T nr = T(0);
       cx<T> c = mk<T>(1, 0), s = mk<T>(0, 0);
-      if (nr2 != T(0)) { const T inr = rsqrt_hd(nr2); nr = nr2 * inr; c = f * inr; s = gg * inr; }
+      if (nr2 > nb_floor<T>::v()) { const T inr = rsq_nb(nr2); nr = nr2 * inr; c = f * inr; s = gg * inr; }   // rsq_nb: no slow-path call
       rc[i] = c; rs[i] = s;
 #pragma unroll
       for (int j = i; j <= EN; ++j) {
@@ -138,9 +138,9 @@ template <typename T, int EN> QMPS_HD int fpd2_stage(cx<T> (&H)[4][4], cx<T> (&w
       const cx<T> bc = b * c;
       if (bc.re != T(0) || bc.im != T(0)) {
         const cx<T> y = (a - d) * T(0.5);
-        cx<T> z = csqrt(y * y + bc);
+        cx<T> z = csqrt_nb(y * y + bc);
         if (y.re * z.re + y.im * z.im < T(0)) z = -z;
-        sh = d - cdiv(bc, y + z);
+        sh = d - cdiv_nb(bc, y + z);
       }
     }
 #pragma unroll

@@ -307,9 +307,9 @@ fp64p_qr_kernel(FpParams p) {
           const cx<T> bc = b * c;
           if (bc.re != T(0) || bc.im != T(0)) {
             const cx<T> y = (a - dd) * T(0.5);
-            cx<T> z = csqrt(y * y + bc);
+            cx<T> z = csqrt_nb(y * y + bc);
             if (y.re * z.re + y.im * z.im < T(0)) z = -z;
-            sigma = dd - cdiv(bc, y + z);
+            sigma = dd - cdiv_nb(bc, y + z);
           }
         }
       }
